@@ -1,0 +1,164 @@
+/*
+ * vkgsb.h — C ABI of the B200-native vkgs renderer path (libvkgsb.so).
+ *
+ * Drop-in boundary for the reference's per-frame hot path: everything below is what a binding of
+ * jaesung-cs/vkgs would call instead of recording Vulkan commands in Engine::Impl::Draw()
+ * (src/vkgs/engine/engine.cc:742-1378).  Plain pointers and sizes only; no C++/torch types.
+ * All functions return VKGSB_OK (0) or an error code; vkgsb_last_error() gives the text of the
+ * calling thread's last failure.  No exception crosses this boundary.  There is no CPU fallback:
+ * without a CUDA device vkgsb_create fails with VKGSB_ERR_CUDA.
+ *
+ * Threading (same contract as the reference): one renderer = one CUDA device + one
+ * stream; draw/set_* are not re-entrant per renderer; load_ply_async / load_progress / cancel_load
+ * may be called from any thread.
+ *
+ * Matrices are column-major float[16] (m[c*4+r]) exactly as glm / the reference's UBO
+ * (src/vkgs/vulkan/shader/uniforms.h:10-15).
+ */
+#ifndef VKGSB_H_
+#define VKGSB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VKGSB_API __declspec(dllexport)
+#else
+#define VKGSB_API __attribute__((visibility("default")))
+#endif
+
+typedef struct vkgsb_renderer vkgsb_renderer;
+
+enum vkgsb_status {
+  VKGSB_OK = 0,
+  VKGSB_ERR_INVALID = 1,  /* bad argument */
+  VKGSB_ERR_CUDA = 2,     /* CUDA runtime / no device */
+  VKGSB_ERR_IO = 3,       /* file open / read / malformed PLY */
+  VKGSB_ERR_CAPACITY = 4, /* more splats than max_splats, image larger than allocated */
+  VKGSB_ERR_NO_SCENE = 5, /* draw before any splats were loaded */
+  VKGSB_ERR_CANCELLED = 6 /* load cancelled */
+};
+
+/* How destination colour is accumulated (SURVEY.md §7 hard part 1). */
+enum vkgsb_blend_mode {
+  VKGSB_BLEND_FP32 = 0,  /* fp32 accumulation, one UNORM8 quantisation at the end; front-to-back with early exit */
+  VKGSB_BLEND_UNORM8 = 1 /* the reference's render target (render_pass.cc:15): destination re-quantised to
+                            UNORM8 after every splat, back-to-front, no early exit */
+};
+
+enum vkgsb_pixel_format {
+  VKGSB_FORMAT_RGBA8 = 0,
+  VKGSB_FORMAT_BGRA8 = 1 /* memory order of the reference's swapchain image (swapchain.cc:18) */
+};
+
+typedef struct vkgsb_config {
+  uint32_t struct_size; /* = sizeof(vkgsb_config) */
+  int32_t device;       /* CUDA device ordinal */
+  uint32_t max_splats;  /* storage is pre-allocated once, like the reference's MAX_SPLAT_COUNT (engine.cc:1653);
+                           0 => 1<<23 */
+  uint32_t max_width;   /* 0 => 3840 */
+  uint32_t max_height;  /* 0 => 2160 */
+  uint64_t max_pairs;   /* capacity of the (tile, splat) binning list; 0 => 16 * max_splats */
+} vkgsb_config;
+
+/* The per-frame parameter block: shader::Camera (uniforms.h:10-15) + the `mat4 model` push constant
+ * (engine.cc:1024-1025,1185-1186). */
+typedef struct vkgsb_camera {
+  float projection[16];
+  float view[16];
+  float camera_position[3];
+  float pad0;
+  float model[16];
+} vkgsb_camera;
+
+/* Mirrors FrameInfo (engine.cc:1620-1636).  Stage times are only filled when stage timing is enabled. */
+typedef struct vkgsb_stats {
+  uint32_t total_point_count;
+  uint32_t loaded_point_count;
+  uint32_t visible_point_count; /* V of the last drawn frame */
+  uint32_t pair_overflow;       /* 1 if the binning list hit max_pairs (farthest splats were dropped) */
+  uint64_t pair_count;          /* (tile, splat) pairs of the last frame */
+  float ms_project;             /* rank.comp + projection.comp equivalent */
+  float ms_sort;                /* vrdxCmdSortKeyValueIndirect equivalent */
+  float ms_bin;                 /* tile binning (no reference equivalent: replaces the HW rasteriser's setup) */
+  float ms_blend;               /* splat.vert/.frag + ROP equivalent */
+  float ms_total;
+  uint64_t frame_counter;
+} vkgsb_stats;
+
+enum vkgsb_option {
+  VKGSB_OPT_STAGE_TIMING = 0, /* 1: launch stages eagerly with CUDA events between them; 0: one CUDA graph per frame */
+  VKGSB_OPT_BLEND_MODE = 1,   /* vkgsb_blend_mode */
+  VKGSB_OPT_PIXEL_FORMAT = 2, /* vkgsb_pixel_format */
+  VKGSB_OPT_BAND_Y0 = 3,      /* restrict binning + blending to image rows [y0,y1) (tile-band sharding) */
+  VKGSB_OPT_BAND_Y1 = 4       /* 0 => full height */
+};
+
+VKGSB_API const char* vkgsb_last_error(void);
+VKGSB_API int vkgsb_device_count(int* count);
+
+/* Engine::Engine() (engine.cc:114-524): allocate every buffer once. */
+VKGSB_API int vkgsb_create(int device, uint32_t max_splats, vkgsb_renderer** out);
+VKGSB_API int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out);
+VKGSB_API void vkgsb_destroy(vkgsb_renderer* r);
+VKGSB_API int vkgsb_set_option(vkgsb_renderer* r, int option, int64_t value);
+
+/* Engine::LoadSplats (engine.cc:541-544) + SplatLoadThread (splat_load_thread.cc:55-207) + parse_ply.comp.
+ * vkgsb_load_ply blocks until the scene is resident; _async returns at once, cancelling a load in flight. */
+VKGSB_API int vkgsb_load_ply(vkgsb_renderer* r, const char* path);
+VKGSB_API int vkgsb_load_ply_async(vkgsb_renderer* r, const char* path);
+/* SplatLoadThread::GetProgress (splat_load_thread.h:35-39).  state: 0 idle, 1 loading, 2 done, <0 -vkgsb_status. */
+VKGSB_API int vkgsb_load_progress(vkgsb_renderer* r, uint32_t* total, uint32_t* loaded, int* state);
+VKGSB_API int vkgsb_cancel_load(vkgsb_renderer* r);
+VKGSB_API int vkgsb_wait_load(vkgsb_renderer* r);
+
+/* Same ingest without a file: `rows` = n PLY vertices as floats (host memory), `offsets` = the 60-entry
+ * float-offset table of splat_load_thread.cc:114-135 (offsets[59] = row stride in floats). */
+VKGSB_API int vkgsb_upload_splats(vkgsb_renderer* r, uint32_t n, const float* rows, const uint32_t offsets[60]);
+
+/* Write the camera UBO + model push constant (engine.cc:1047-1050,1185-1186) and the viewport (engine.cc:1419-1431). */
+VKGSB_API int vkgsb_set_camera(vkgsb_renderer* r, const vkgsb_camera* cam);
+VKGSB_API int vkgsb_set_viewport(vkgsb_renderer* r, uint32_t width, uint32_t height);
+
+/* One frame: rank -> sort -> projection -> draw (engine.cc:1164-1290), into an RGBA8/BGRA8 image of
+ * width*height*4 bytes.  dst may be NULL (image stays in the renderer, see vkgsb_image_device_ptr), a host pointer
+ * (dst_is_device = 0: device->host copy, returns when the pixels are in dst) or a device pointer (dst_is_device = 1:
+ * asynchronous on `stream`).  stream = a cudaStream_t cast to void*, NULL = the renderer's own stream. */
+VKGSB_API int vkgsb_draw(vkgsb_renderer* r, void* dst, int dst_is_device, void* stream);
+/* n_views frames with one scene: cameras[i] -> dst + i*stride bytes (same dst rules). */
+VKGSB_API int vkgsb_draw_batch(vkgsb_renderer* r, uint32_t n_views, const vkgsb_camera* cameras, void* dst,
+                               size_t dst_stride, int dst_is_device, void* stream);
+VKGSB_API int vkgsb_image_device_ptr(vkgsb_renderer* r, void** ptr);
+VKGSB_API int vkgsb_sync(vkgsb_renderer* r);
+VKGSB_API int vkgsb_get_stats(vkgsb_renderer* r, vkgsb_stats* out);
+
+/* Parity taps (test / debugging): state of the last drawn frame, copied to host.
+ * read_sorted: keys/ids in sorted (far -> near) order = SplatStorage.key / .index after vrdx (engine.cc:1218-1219).
+ * read_instances: 12 floats per visible splat in sorted order = SplatStorage.instance (projection.comp:177-179).
+ * read_scene: the activated scene in the reference layout (engine.cc:1639-1651): pos[n*3], cov[n*6],
+ *             opacity[n], sh[n*48] (IEEE half bits). Any pointer may be NULL. */
+VKGSB_API int vkgsb_read_sorted(vkgsb_renderer* r, uint32_t* keys, uint32_t* ids, uint32_t capacity, uint32_t* count);
+VKGSB_API int vkgsb_read_instances(vkgsb_renderer* r, float* inst, uint32_t capacity, uint32_t* count);
+VKGSB_API int vkgsb_read_scene(vkgsb_renderer* r, float* pos, float* cov, float* opacity, uint16_t* sh,
+                               uint32_t capacity, uint32_t* count);
+
+/* Stage-level plug-in for the sort alone, the vrdx* surface of third_party/vulkan_radix_sort
+ * (include/vk_radix_sort.h:19-76): ascending, stable, in place, element count read ON THE DEVICE from d_count
+ * (vrdxCmdSortKeyValueIndirect), caller-owned storage from vkgsb_sort_storage_bytes
+ * (vrdxGetSorterKeyValueStorageRequirements).  All pointers are device pointers; asynchronous on `stream`. */
+VKGSB_API int vkgsb_sort_storage_bytes(uint32_t max_element_count, size_t* bytes);
+VKGSB_API int vkgsb_sort_key_value_indirect(void* stream, uint32_t max_element_count, const uint32_t* d_count,
+                                            uint32_t* d_keys, uint32_t* d_values, void* d_storage);
+
+/* Host helper: vkgs::Camera (camera.cc:25-45) for an orbit pose; fills projection/view/camera_position, model = I. */
+VKGSB_API int vkgsb_camera_orbit(uint32_t width, uint32_t height, float fovy, float r, float phi, float theta,
+                                 const float center[3], vkgsb_camera* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKGSB_H_ */

@@ -1,0 +1,88 @@
+"""Build libvkgsb.so (CUDA kernels + C ABI + C++ facade) in-tree for sm_100a.
+
+    python -m vkgs_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The library links the CUDA runtime statically, so it coexists with the runtime
+PyTorch bundles.  project.cu and load.cu are compiled with -fmad=false: their arithmetic is pinned operation by
+operation to oracle/vkgs_oracle.c (bit-exact visible set, keys and instance records).
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "lib", "obj")
+LIB = os.path.join(HERE, "lib", "libvkgsb.so")
+
+NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+          "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-Wall,-Wno-unused-function",
+          "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+
+# source -> extra flags
+SOURCES = {
+    "project.cu": ["-fmad=false"],
+    "load.cu": ["-fmad=false"],
+    "sort.cu": [],
+    "bin.cu": [],
+    "blend.cu": [],
+    "renderer.cu": [],
+    "ply.cc": [],
+    "camera.cc": [],
+    "engine.cc": [],
+}
+HEADERS = ["common.cuh", "kernels.h", "hostmath.h", "ply.h", os.path.join(ROOT, "include", "vkgsb.h"),
+           os.path.join(ROOT, "include", "vkgs", "engine", "engine.h"),
+           os.path.join(ROOT, "include", "vkgs", "scene", "camera.h")]
+
+
+def _newest_header() -> float:
+    t = os.path.getmtime(os.path.abspath(__file__))
+    for h in HEADERS:
+        p = h if os.path.isabs(h) else os.path.join(CSRC, h)
+        if os.path.exists(p):
+            t = max(t, os.path.getmtime(p))
+    return t
+
+
+def _compile(src: str, flags, force: bool, hdr_time: float, verbose: bool):
+    path = os.path.join(CSRC, src)
+    obj = os.path.join(OBJ, src + ".o")
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(path), hdr_time):
+        return obj, ""
+    cmd = [NVCC, *ARCH, *COMMON, *flags, "-Xptxas", "-v", "-c", path, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return obj, r.stderr if verbose else ""
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = {s: f for s, f in SOURCES.items() if os.path.exists(os.path.join(CSRC, s))}
+    hdr_time = _newest_header()
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        futs = [ex.submit(_compile, s, f, force, hdr_time, verbose) for s, f in srcs.items()]
+        results = [f.result() for f in futs]
+    objs = [o for o, _ in results]
+    if verbose:
+        for _, log in results:
+            if log:
+                sys.stderr.write(log)
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        cmd = [NVCC, *ARCH, "-shared", "-cudart", "static", "-o", LIB, *objs, "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv or "--verbose" in sys.argv))

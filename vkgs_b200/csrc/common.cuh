@@ -1,0 +1,112 @@
+// Shared device-side declarations of the vkgs_b200 frame pipeline (sm_100a).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vkgsb {
+
+constexpr int kTile = 16;              // blend tile edge in pixels (also the origin of the pinned fragment arithmetic)
+constexpr int VKGSB_BLEND_FP32_MODE = 0, VKGSB_BLEND_UNORM8_MODE = 1;  // == enum vkgsb_blend_mode (include/vkgsb.h)
+
+// ---- resident scene (HBM layout) ---------------------------------------------------------------
+// Positions are planar so the cull pass streams 12 B/splat fully coalesced; everything only a *visible* splat needs
+// is one 128-byte line.
+struct __align__(16) SplatPayload {
+  float cov[6];   // c00 c10 c20 c11 c21 c22  (parse_ply.comp:80-85)
+  float opacity;  // post-sigmoid
+  float pad;
+  __half sh[48];  // channel-major [3][16]     (projection.comp:31-33,165-168)
+};
+static_assert(sizeof(SplatPayload) == 128, "payload must be one 128-byte line");
+
+struct Scene {
+  const float* x;
+  const float* y;
+  const float* z;
+  const SplatPayload* payload;
+  uint32_t n;
+};
+
+// ---- per-frame parameter block (device copy of uniforms.h:10-15 + derived values) ----------------------------
+struct FrameParams {
+  float proj[16];
+  float view[16];
+  float model[16];
+  float pvm[16];        // (proj*view)*model composed on the host, rank.comp:32
+  float cam_model[3];   // inverse(model)*eye / w, projection.comp:85-86 hoisted
+  float inv_w, inv_h;   // unused by pinned math (kept for tools)
+  uint32_t width, height;
+  uint32_t tiles_x, tiles_y;
+  uint32_t band_y0, band_y1;  // rows [y0,y1) this renderer bins and blends
+  uint32_t tile_y0, tile_y1;  // tile rows covering the band
+};
+
+// ---- control block: everything the host zeroes with one memset per frame --------------------------------------
+struct Control {
+  uint32_t visible_count;   // V  (VisiblePointCount, rank.comp:38)
+  uint32_t pair_count;      // D
+  uint32_t pair_overflow;
+  uint32_t project_ticket;
+  uint32_t pairs_ticket;
+  uint32_t sort_ticket[8];  // [0..3] depth passes, [4..7] tile passes
+  uint32_t pad[3];
+  uint32_t hist_depth[4 * 256];
+  uint32_t hist_tile[4 * 256];
+};
+
+// ---- decoupled look-back descriptor for the two ordered block scans (visible slots, pair offsets) --------------
+// 64-bit word: low 32 = value, high 32 = status (0 = invalid, 1 = aggregate, 2 = inclusive prefix).
+constexpr uint32_t kScanAggregate = 1u, kScanInclusive = 2u;
+
+__device__ __forceinline__ void scan_publish(unsigned long long* d, uint32_t status, uint32_t value) {
+  unsigned long long w = (static_cast<unsigned long long>(status) << 32) | value;
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(d), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long scan_peek(const unsigned long long* d) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(d) : "memory");
+  return w;
+}
+
+// Exclusive prefix of `block_total` over all blocks with a smaller ticket.  Call from ONE full warp (warp-uniform
+// ticket); every lane returns the prefix.  Publishes this block's aggregate, walks back 32 descriptors at a time,
+// then publishes the inclusive value.
+__device__ __forceinline__ uint32_t scan_lookback_warp(unsigned long long* desc, uint32_t ticket, uint32_t block_total) {
+  const uint32_t lane = threadIdx.x & 31u;
+  if (ticket == 0) {
+    if (lane == 0) scan_publish(desc, kScanInclusive, block_total);
+    return 0u;
+  }
+  if (lane == 0) scan_publish(desc + ticket, kScanAggregate, block_total);
+  uint32_t prefix = 0;
+  int64_t hi = static_cast<int64_t>(ticket) - 1;  // newest descriptor not yet consumed
+  while (true) {
+    int64_t idx = hi - lane;
+    unsigned long long w = 0;
+    uint32_t st = kScanInclusive;  // lanes before descriptor 0 act as a zero inclusive terminator
+    uint32_t val = 0;
+    if (idx >= 0) {
+      do {
+        w = scan_peek(desc + idx);
+        st = static_cast<uint32_t>(w >> 32);
+      } while (st == 0u);
+      val = static_cast<uint32_t>(w);
+    }
+    // first lane (nearest predecessor side) holding an inclusive value terminates the walk
+    uint32_t incl_mask = __ballot_sync(0xffffffffu, st == kScanInclusive);
+    uint32_t first = __ffs(incl_mask) - 1;  // incl_mask != 0 guaranteed once idx < 0 lanes exist or found
+    if (incl_mask == 0u) first = 32u;
+    uint32_t contrib = (lane <= first) ? val : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+    prefix += contrib;
+    if (incl_mask != 0u) break;
+    hi -= 32;
+  }
+  if (lane == 0) scan_publish(desc + ticket, kScanInclusive, prefix + block_total);
+  return prefix;
+}
+
+}  // namespace vkgsb

@@ -1,0 +1,67 @@
+// Host-side launch interface of the stage kernels (one .cu per stage).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace vkgsb {
+
+// ---- load.cu: parse_ply.comp equivalent + parity tap ---------------------------------------------------------
+struct SceneStorage {
+  float* x;
+  float* y;
+  float* z;
+  SplatPayload* payload;
+};
+// rows: `count` PLY vertices already on the device; offsets: 60-entry table on the device.  Writes splats
+// [first, first+count).
+void launch_activate(const float* d_rows, const uint32_t* d_offsets, uint32_t first, uint32_t count,
+                     const SceneStorage& dst, cudaStream_t stream);
+// back to the reference layout (engine.cc:1639-1651); any destination may be null.
+void launch_export_scene(const SceneStorage& src, uint32_t n, float* d_pos, float* d_cov, float* d_opacity,
+                         uint16_t* d_sh, cudaStream_t stream);
+
+// ---- project.cu ------------------------------------------------------------------------------------------------
+uint32_t project_num_blocks(uint32_t n);
+void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl, unsigned long long* d_scan_desc,
+                    uint32_t* d_keys, uint32_t* d_slots, uint32_t* d_vis_id, float* d_inst, cudaStream_t stream);
+
+// ---- sort.cu: onesweep LSD radix sort, count read on the device ----------------------------------------------------
+struct SortArgs {
+  const uint32_t* d_count;  // element count (device)
+  uint32_t max_n;           // capacity the launch is sized for
+  uint32_t* keys;           // in/out (result lands here: the pass count is even)
+  uint32_t* vals;
+  uint32_t* keys_alt;       // ping-pong scratch, max_n each
+  uint32_t* vals_alt;
+  uint32_t* hist;           // [npass][256], zero on entry
+  uint32_t* tickets;        // [npass], zero on entry
+  uint32_t* lookback;       // [npass][sort_max_parts(max_n)][256]; cleared by the histogram kernel
+  int begin_bit;            // first pass digit starts here; passes are 8 bits wide
+  int npass;                // 2 or 4
+};
+uint32_t sort_max_parts(uint32_t max_n);
+size_t sort_lookback_bytes(uint32_t max_n, int npass);
+void launch_sort(const SortArgs& a, cudaStream_t stream);
+
+// ---- bin.cu: (tile, splat) pairs in front-to-back order + per-tile ranges ------------------------------------------
+uint32_t pairs_num_blocks(uint32_t max_visible);
+void launch_make_pairs(const FrameParams* d_fp, Control* d_ctrl, unsigned long long* d_scan_desc,
+                       const uint32_t* d_sorted_slots, const float* d_inst, uint32_t max_visible, uint64_t max_pairs,
+                       uint32_t* d_pair_tile, uint32_t* d_pair_slot, cudaStream_t stream);
+void launch_tile_ranges(const Control* d_ctrl, const uint32_t* d_pair_tile_sorted, uint64_t max_pairs,
+                        uint2* d_ranges, cudaStream_t stream);
+
+// ---- blend.cu ------------------------------------------------------------------------------------------------------
+void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_slot,
+                  const float* d_inst, int blend_mode, int bgra, uint8_t* d_image, cudaStream_t stream);
+
+// ---- misc ----------------------------------------------------------------------------------------------------------
+void launch_gather_sorted(const Control* d_ctrl, const uint32_t* d_sorted_slots, const uint32_t* d_vis_id,
+                          const float* d_inst, uint32_t max_visible, uint32_t* d_ids_out, float* d_inst_out,
+                          cudaStream_t stream);
+
+}  // namespace vkgsb

@@ -1,0 +1,725 @@
+// C ABI (include/vkgsb.h) and frame orchestration: the CUDA counterpart of Engine::Impl (engine.cc:114-524 buffers,
+// 742-1378 Draw) without the window, swapchain and UI.  One renderer = one device, one render stream, one loader
+// thread.  Storage is allocated once in vkgsb_create (the reference pre-allocates for MAX_SPLAT_COUNT,
+// engine.cc:483-502); per frame the host sends the parameter block (256 B in the reference's UBO + push constant,
+// here one kernel-argument upload), clears a ~0.6 MB control region and replays a CUDA graph of the stage kernels.
+// Counts (visible splats, pairs) never come back to the host on the critical path, like the reference's indirect
+// dispatch (engine.cc:1218-1219, projection.comp:64-75).
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/vkgsb.h"
+#include "hostmath.h"
+#include "kernels.h"
+#include "ply.h"
+
+using namespace vkgsb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                  \
+  do {                                                                                                \
+    cudaError_t e_ = (expr);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(VKGSB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+__global__ void k_set_params(FrameParams p, FrameParams* dst) {
+  if (threadIdx.x == 0) *dst = p;
+}
+
+constexpr uint32_t kChunkVertices = 65536;  // splat_load_thread.cc:140
+
+}  // namespace
+
+struct vkgsb_renderer {
+  int device = 0;
+  uint32_t max_splats = 0, max_width = 0, max_height = 0;
+  uint64_t max_pairs = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t load_stream = nullptr;
+
+  // resident scene
+  SceneStorage scene{};
+  std::atomic<uint32_t> scene_n{0};
+
+  // per-frame work buffers
+  uint32_t *keys = nullptr, *slots = nullptr, *keys_alt = nullptr, *slots_alt = nullptr, *vis_id = nullptr;
+  float* inst = nullptr;
+  uint32_t *pair_tile = nullptr, *pair_slot = nullptr, *pair_tile_alt = nullptr, *pair_slot_alt = nullptr;
+  uint32_t *lookback_depth = nullptr, *lookback_tile = nullptr;
+  uint8_t* zero_region = nullptr;  // Control | scan descriptors (project) | scan descriptors (pairs) | tile ranges
+  size_t zero_bytes = 0;
+  Control* ctrl = nullptr;
+  unsigned long long *desc_project = nullptr, *desc_pairs = nullptr;
+  uint2* ranges = nullptr;
+  FrameParams* d_fp = nullptr;
+  uint8_t* image = nullptr;
+  uint32_t* h_counts = nullptr;  // pinned: visible, pairs, overflow of the last frame
+
+  // load staging
+  float* d_rows[2] = {nullptr, nullptr};
+  float* h_rows[2] = {nullptr, nullptr};
+  size_t rows_capacity_bytes = 0;
+  uint32_t* d_offsets = nullptr;
+  cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+
+  // frame state
+  vkgsb_camera cam{};
+  bool have_cam = false;
+  uint32_t width = 0, height = 0;
+  int blend_mode = VKGSB_BLEND_FP32, pixel_format = VKGSB_FORMAT_RGBA8, stage_timing = 0;
+  uint32_t band_y0 = 0, band_y1 = 0;
+  FrameParams h_fp{};
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_valid = false;
+  uint32_t graph_n = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_recorded = false;
+  uint64_t frame_counter = 0;
+  std::mutex draw_mutex;
+
+  // loader thread (SplatLoadThread)
+  std::thread loader;
+  std::mutex load_mutex;
+  std::condition_variable load_cv;
+  std::string pending_path;
+  bool loader_exit = false;
+  std::atomic<bool> cancel{false};
+  std::atomic<uint32_t> total_points{0}, loaded_points{0};
+  std::atomic<int> load_state{0};  // 0 idle, 1 loading, 2 done, <0 error
+  std::string load_error;
+};
+
+namespace {
+
+int set_device(vkgsb_renderer* r) {
+  CU_TRY(cudaSetDevice(r->device));
+  return VKGSB_OK;
+}
+
+void invalidate_graph(vkgsb_renderer* r) { r->graph_valid = false; }
+
+int ensure_row_staging(vkgsb_renderer* r, uint32_t stride_bytes) {
+  size_t need = static_cast<size_t>(kChunkVertices) * stride_bytes;
+  if (need <= r->rows_capacity_bytes) return VKGSB_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (r->d_rows[i]) cudaFree(r->d_rows[i]);
+    if (r->h_rows[i]) cudaFreeHost(r->h_rows[i]);
+    r->d_rows[i] = nullptr;
+    r->h_rows[i] = nullptr;
+  }
+  r->rows_capacity_bytes = 0;
+  for (int i = 0; i < 2; ++i) {
+    CU_TRY(cudaMalloc(&r->d_rows[i], need));
+    CU_TRY(cudaMallocHost(&r->h_rows[i], need));
+  }
+  r->rows_capacity_bytes = need;
+  return VKGSB_OK;
+}
+
+// Streamed ingest shared by upload_splats (memory source) and load_ply (file source): 65 536-vertex chunks through
+// two pinned buffers, H2D and activation of chunk k overlapping the host fill of chunk k+1.
+// fill(dst, first_vertex, count) returns false on a short read.
+template <class Fill>
+int ingest(vkgsb_renderer* r, uint64_t n64, uint32_t stride_bytes, const uint32_t offsets[60], Fill fill) {
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  if (n64 > r->max_splats)
+    return fail(VKGSB_ERR_CAPACITY, "scene has " + std::to_string(n64) + " splats, renderer was created for " +
+                                        std::to_string(r->max_splats));
+  const uint32_t n = static_cast<uint32_t>(n64);
+  if (int e = ensure_row_staging(r, stride_bytes)) return e;
+  {
+    // the resident scene is rewritten in place: retire it and drain frames that still read it
+    std::lock_guard<std::mutex> g(r->draw_mutex);
+    r->scene_n.store(0);
+    invalidate_graph(r);
+    CU_TRY(cudaStreamSynchronize(r->stream));
+  }
+  r->total_points.store(n);
+  r->loaded_points.store(0);
+  CU_TRY(cudaMemcpyAsync(r->d_offsets, offsets, 60 * sizeof(uint32_t), cudaMemcpyHostToDevice, r->load_stream));
+  CU_TRY(cudaStreamSynchronize(r->load_stream));  // offsets may live on the caller's stack
+  int buf = 0;
+  for (uint64_t start = 0; start < n; start += kChunkVertices, buf ^= 1) {
+    if (r->cancel.load()) {
+      cudaStreamSynchronize(r->load_stream);
+      return fail(VKGSB_ERR_CANCELLED, "load cancelled");
+    }
+    const uint32_t count = static_cast<uint32_t>(std::min<uint64_t>(kChunkVertices, n - start));
+    CU_TRY(cudaEventSynchronize(r->chunk_done[buf]));  // staging buffer free again
+    if (!fill(r->h_rows[buf], start, count)) {
+      cudaStreamSynchronize(r->load_stream);
+      return fail(VKGSB_ERR_IO, "short read at vertex " + std::to_string(start));
+    }
+    CU_TRY(cudaMemcpyAsync(r->d_rows[buf], r->h_rows[buf], static_cast<size_t>(count) * stride_bytes,
+                           cudaMemcpyHostToDevice, r->load_stream));
+    launch_activate(r->d_rows[buf], r->d_offsets, static_cast<uint32_t>(start), count, r->scene, r->load_stream);
+    CU_TRY(cudaEventRecord(r->chunk_done[buf], r->load_stream));
+    r->loaded_points.store(static_cast<uint32_t>(start + count));
+  }
+  CU_TRY(cudaStreamSynchronize(r->load_stream));
+  CU_TRY(cudaGetLastError());
+  {
+    std::lock_guard<std::mutex> g(r->draw_mutex);
+    r->scene_n.store(n);
+    invalidate_graph(r);
+  }
+  return VKGSB_OK;
+}
+
+int load_file(vkgsb_renderer* r, const std::string& path) {
+  PlyHeader h;
+  std::string err = parse_ply_header(path, &h);
+  if (!err.empty()) return fail(VKGSB_ERR_IO, path + ": " + err);
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return fail(VKGSB_ERR_IO, "cannot open " + path);
+  // 64-bit offsets: the reference's `offset * start` is 32-bit and wraps past 4 GiB (splat_load_thread.cc:145)
+  if (fseeko(f, static_cast<off_t>(h.body_offset), SEEK_SET) != 0) {
+    std::fclose(f);
+    return fail(VKGSB_ERR_IO, "seek failed in " + path);
+  }
+  int rc = ingest(r, h.vertex_count, h.stride_bytes, h.offsets, [&](float* dst, uint64_t, uint32_t count) {
+    size_t want = static_cast<size_t>(count) * h.stride_bytes;
+    return std::fread(dst, 1, want, f) == want;
+  });
+  std::fclose(f);
+  return rc;
+}
+
+void loader_main(vkgsb_renderer* r) {
+  while (true) {
+    std::string path;
+    {
+      std::unique_lock<std::mutex> g(r->load_mutex);
+      r->load_cv.wait(g, [r] { return r->loader_exit || !r->pending_path.empty(); });
+      if (r->loader_exit) return;
+      path = std::move(r->pending_path);
+      r->pending_path.clear();
+      r->cancel.store(false);
+      r->load_state.store(1);
+    }
+    int rc = load_file(r, path);
+    {
+      std::unique_lock<std::mutex> g(r->load_mutex);
+      if (rc != VKGSB_OK) r->load_error = g_last_error;
+      // a newer request supersedes this result
+      if (r->pending_path.empty()) r->load_state.store(rc == VKGSB_OK ? 2 : -rc);
+    }
+    r->load_cv.notify_all();
+  }
+}
+
+void fill_params(vkgsb_renderer* r) {
+  FrameParams& p = r->h_fp;
+  std::memcpy(p.proj, r->cam.projection, 64);
+  std::memcpy(p.view, r->cam.view, 64);
+  std::memcpy(p.model, r->cam.model, 64);
+  float pv[16];
+  mat4_mul(p.proj, p.view, pv);  // projection * view * model, left to right (rank.comp:32)
+  mat4_mul(pv, p.model, p.pvm);
+  float inv[16], e[4] = {r->cam.camera_position[0], r->cam.camera_position[1], r->cam.camera_position[2], 1.f}, cm[4];
+  mat4_inverse(p.model, inv);  // inverse(model) * vec4(camera_position, 1), hoisted (projection.comp:85-86)
+  mat4_vec(inv, e, cm);
+  p.cam_model[0] = cm[0] / cm[3];
+  p.cam_model[1] = cm[1] / cm[3];
+  p.cam_model[2] = cm[2] / cm[3];
+  p.width = r->width;
+  p.height = r->height;
+  p.inv_w = 1.f / static_cast<float>(r->width);
+  p.inv_h = 1.f / static_cast<float>(r->height);
+  p.tiles_x = (r->width + kTile - 1) / kTile;
+  p.tiles_y = (r->height + kTile - 1) / kTile;
+  p.band_y0 = std::min(r->band_y0, r->height);
+  p.band_y1 = (r->band_y1 == 0 || r->band_y1 > r->height) ? r->height : r->band_y1;
+  if (p.band_y1 < p.band_y0) p.band_y1 = p.band_y0;
+  p.tile_y0 = p.band_y0 / kTile;
+  p.tile_y1 = (p.band_y1 + kTile - 1) / kTile;
+  if (p.band_y1 == p.band_y0) p.tile_y1 = p.tile_y0;
+}
+
+// Stage kernels of one frame on `s`.  With `timed`, CUDA events bracket the stages (ev[0..4]).
+int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
+  const uint32_t n = r->scene_n.load();
+  Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.payload, n};
+  CU_TRY(cudaMemsetAsync(r->zero_region, 0, r->zero_bytes, s));
+  if (timed) CU_TRY(cudaEventRecord(r->ev[0], s));
+  launch_project(sc, r->d_fp, r->ctrl, r->desc_project, r->keys, r->slots, r->vis_id, r->inst, s);
+  if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
+  SortArgs depth{};
+  depth.d_count = &r->ctrl->visible_count;
+  depth.max_n = n;
+  depth.keys = r->keys; depth.vals = r->slots; depth.keys_alt = r->keys_alt; depth.vals_alt = r->slots_alt;
+  depth.hist = r->ctrl->hist_depth; depth.tickets = r->ctrl->sort_ticket; depth.lookback = r->lookback_depth;
+  depth.begin_bit = 0; depth.npass = 4;
+  launch_sort(depth, s);
+  if (timed) CU_TRY(cudaEventRecord(r->ev[2], s));
+  launch_make_pairs(r->d_fp, r->ctrl, r->desc_pairs, r->slots, r->inst, n, r->max_pairs, r->pair_tile, r->pair_slot, s);
+  SortArgs tiles{};
+  tiles.d_count = &r->ctrl->pair_count;
+  tiles.max_n = static_cast<uint32_t>(r->max_pairs);
+  tiles.keys = r->pair_tile; tiles.vals = r->pair_slot; tiles.keys_alt = r->pair_tile_alt; tiles.vals_alt = r->pair_slot_alt;
+  tiles.hist = r->ctrl->hist_tile; tiles.tickets = r->ctrl->sort_ticket + 4; tiles.lookback = r->lookback_tile;
+  tiles.begin_bit = 0; tiles.npass = 2;  // tile ids < 2^16 (<= 240 x 135 tiles at 3840 x 2160)
+  launch_sort(tiles, s);
+  launch_tile_ranges(r->ctrl, r->pair_tile, r->max_pairs, r->ranges, s);
+  if (timed) CU_TRY(cudaEventRecord(r->ev[3], s));
+  launch_blend(r->d_fp, r->h_fp, r->ranges, r->pair_slot, r->inst, r->blend_mode,
+               r->pixel_format == VKGSB_FORMAT_BGRA8, r->image, s);
+  if (timed) CU_TRY(cudaEventRecord(r->ev[4], s));
+  CU_TRY(cudaMemcpyAsync(r->h_counts, r->ctrl, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaGetLastError());
+  return VKGSB_OK;
+}
+
+int run_frame(vkgsb_renderer* r, cudaStream_t s) {
+  if (!r->have_cam) return fail(VKGSB_ERR_INVALID, "vkgsb_set_camera has not been called");
+  if (r->width == 0 || r->height == 0) return fail(VKGSB_ERR_INVALID, "vkgsb_set_viewport has not been called");
+  const uint32_t n = r->scene_n.load();
+  if (n == 0) return fail(VKGSB_ERR_NO_SCENE, "no splats loaded");
+  fill_params(r);
+  k_set_params<<<1, 32, 0, s>>>(r->h_fp, r->d_fp);
+  if (r->stage_timing) {
+    if (int e = record_stages(r, s, true)) return e;
+    r->ev_recorded = true;
+  } else {
+    // the graph is captured on the renderer's own stream and is valid for one (n, viewport, band, mode, format)
+    if (!r->graph_valid || r->graph_n != n) {
+      if (r->graph_exec) {
+        cudaGraphExecDestroy(r->graph_exec);
+        r->graph_exec = nullptr;
+      }
+      cudaGraph_t graph = nullptr;
+      CU_TRY(cudaStreamBeginCapture(r->stream, cudaStreamCaptureModeThreadLocal));
+      int e = record_stages(r, r->stream, false);
+      cudaError_t ce = cudaStreamEndCapture(r->stream, &graph);
+      if (e) return e;
+      CU_TRY(ce);
+      CU_TRY(cudaGraphInstantiate(&r->graph_exec, graph, 0));
+      cudaGraphDestroy(graph);
+      r->graph_valid = true;
+      r->graph_n = n;
+    }
+    CU_TRY(cudaGraphLaunch(r->graph_exec, s));
+    r->ev_recorded = false;
+  }
+  r->frame_counter++;
+  return VKGSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vkgsb_last_error(void) { return g_last_error.c_str(); }
+
+int vkgsb_device_count(int* count) {
+  if (!count) return fail(VKGSB_ERR_INVALID, "count is null");
+  *count = 0;
+  CU_TRY(cudaGetDeviceCount(count));
+  return VKGSB_OK;
+}
+
+int vkgsb_create(int device, uint32_t max_splats, vkgsb_renderer** out) {
+  vkgsb_config c{};
+  c.struct_size = sizeof(c);
+  c.device = device;
+  c.max_splats = max_splats;
+  return vkgsb_create_ex(&c, out);
+}
+
+int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
+  if (!cfg || !out) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (cfg->struct_size != sizeof(vkgsb_config)) return fail(VKGSB_ERR_INVALID, "vkgsb_config.struct_size mismatch");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(VKGSB_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                    " (this renderer has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(VKGSB_ERR_INVALID, "device ordinal out of range");
+  auto* r = new vkgsb_renderer();
+  r->device = cfg->device;
+  r->max_splats = cfg->max_splats ? cfg->max_splats : (1u << 23);
+  r->max_width = cfg->max_width ? cfg->max_width : 3840;
+  r->max_height = cfg->max_height ? cfg->max_height : 2160;
+  r->max_pairs = cfg->max_pairs ? cfg->max_pairs : 16ull * r->max_splats;
+  if (r->max_pairs > (1ull << 31)) r->max_pairs = 1ull << 31;
+  if (r->max_pairs < 4096) r->max_pairs = 4096;
+
+  auto bail = [&](const std::string& what, cudaError_t ce) {
+    std::string msg = what + ": " + cudaGetErrorString(ce);
+    vkgsb_destroy(r);
+    return fail(VKGSB_ERR_CUDA, msg);
+  };
+#define ALLOC(ptr, bytes)                                                  \
+  do {                                                                     \
+    cudaError_t ce_ = cudaMalloc(reinterpret_cast<void**>(&(ptr)), bytes); \
+    if (ce_ != cudaSuccess) return bail("cudaMalloc " #ptr, ce_);          \
+  } while (0)
+
+  if ((e = cudaSetDevice(r->device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&r->load_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  const size_t N = r->max_splats, P = r->max_pairs;
+  ALLOC(r->scene.x, N * 4); ALLOC(r->scene.y, N * 4); ALLOC(r->scene.z, N * 4);
+  ALLOC(r->scene.payload, N * sizeof(SplatPayload));
+  ALLOC(r->keys, N * 4); ALLOC(r->slots, N * 4); ALLOC(r->keys_alt, N * 4); ALLOC(r->slots_alt, N * 4);
+  ALLOC(r->vis_id, N * 4);
+  ALLOC(r->inst, N * 48);
+  ALLOC(r->pair_tile, P * 4); ALLOC(r->pair_slot, P * 4); ALLOC(r->pair_tile_alt, P * 4); ALLOC(r->pair_slot_alt, P * 4);
+  ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats, 4));
+  ALLOC(r->lookback_tile, sort_lookback_bytes(static_cast<uint32_t>(P), 2));
+  const size_t max_tiles = static_cast<size_t>((r->max_width + kTile - 1) / kTile) * ((r->max_height + kTile - 1) / kTile);
+  const size_t nb_proj = project_num_blocks(r->max_splats), nb_pairs = pairs_num_blocks(r->max_splats);
+  const size_t ctrl_bytes = (sizeof(Control) + 255) & ~size_t(255);
+  r->zero_bytes = ctrl_bytes + (nb_proj + nb_pairs) * 8 + max_tiles * sizeof(uint2);
+  ALLOC(r->zero_region, r->zero_bytes);
+  r->ctrl = reinterpret_cast<Control*>(r->zero_region);
+  r->desc_project = reinterpret_cast<unsigned long long*>(r->zero_region + ctrl_bytes);
+  r->desc_pairs = r->desc_project + nb_proj;
+  r->ranges = reinterpret_cast<uint2*>(r->desc_pairs + nb_pairs);
+  ALLOC(r->d_fp, sizeof(FrameParams));
+  ALLOC(r->image, static_cast<size_t>(r->max_width) * r->max_height * 4);
+  ALLOC(r->d_offsets, 60 * 4);
+#undef ALLOC
+  if ((e = cudaMallocHost(reinterpret_cast<void**>(&r->h_counts), 64)) != cudaSuccess) return bail("cudaMallocHost", e);
+  std::memset(r->h_counts, 0, 64);
+  for (auto& ev : r->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  for (auto& ev : r->chunk_done)
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  r->loader = std::thread(loader_main, r);
+  *out = r;
+  return VKGSB_OK;
+}
+
+void vkgsb_destroy(vkgsb_renderer* r) {
+  if (!r) return;
+  if (r->loader.joinable()) {
+    {
+      std::unique_lock<std::mutex> g(r->load_mutex);
+      r->loader_exit = true;
+      r->cancel.store(true);
+    }
+    r->load_cv.notify_all();
+    r->loader.join();
+  }
+  cudaSetDevice(r->device);
+  if (r->stream) cudaStreamSynchronize(r->stream);
+  if (r->load_stream) cudaStreamSynchronize(r->load_stream);
+  if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
+  void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
+                 r->vis_id, r->inst, r->pair_tile, r->pair_slot, r->pair_tile_alt, r->pair_slot_alt, r->lookback_depth,
+                 r->lookback_tile, r->zero_region, r->d_fp, r->image, r->d_offsets, r->d_rows[0], r->d_rows[1]};
+  for (void* p : dev)
+    if (p) cudaFree(p);
+  if (r->h_counts) cudaFreeHost(r->h_counts);
+  for (auto* p : r->h_rows)
+    if (p) cudaFreeHost(p);
+  for (auto& ev : r->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : r->chunk_done)
+    if (ev) cudaEventDestroy(ev);
+  if (r->stream) cudaStreamDestroy(r->stream);
+  if (r->load_stream) cudaStreamDestroy(r->load_stream);
+  delete r;
+}
+
+int vkgsb_set_option(vkgsb_renderer* r, int option, int64_t value) {
+  if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
+  std::lock_guard<std::mutex> g(r->draw_mutex);
+  switch (option) {
+    case VKGSB_OPT_STAGE_TIMING: r->stage_timing = value != 0; break;
+    case VKGSB_OPT_BLEND_MODE:
+      if (value != VKGSB_BLEND_FP32 && value != VKGSB_BLEND_UNORM8) return fail(VKGSB_ERR_INVALID, "bad blend mode");
+      r->blend_mode = static_cast<int>(value);
+      break;
+    case VKGSB_OPT_PIXEL_FORMAT:
+      if (value != VKGSB_FORMAT_RGBA8 && value != VKGSB_FORMAT_BGRA8) return fail(VKGSB_ERR_INVALID, "bad pixel format");
+      r->pixel_format = static_cast<int>(value);
+      break;
+    case VKGSB_OPT_BAND_Y0: r->band_y0 = static_cast<uint32_t>(value); break;
+    case VKGSB_OPT_BAND_Y1: r->band_y1 = static_cast<uint32_t>(value); break;
+    default: return fail(VKGSB_ERR_INVALID, "unknown option");
+  }
+  invalidate_graph(r);
+  return VKGSB_OK;
+}
+
+int vkgsb_load_ply_async(vkgsb_renderer* r, const char* path) {
+  if (!r || !path) return fail(VKGSB_ERR_INVALID, "null argument");
+  {
+    std::unique_lock<std::mutex> g(r->load_mutex);
+    r->cancel.store(true);  // Cancel(); Start(path)   (engine.cc:541-544)
+    r->pending_path = path;
+    r->load_state.store(1);
+  }
+  r->load_cv.notify_all();
+  return VKGSB_OK;
+}
+
+int vkgsb_wait_load(vkgsb_renderer* r) {
+  if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
+  std::unique_lock<std::mutex> g(r->load_mutex);
+  r->load_cv.wait(g, [r] { return r->load_state.load() != 1; });
+  int st = r->load_state.load();
+  if (st < 0) return fail(-st, r->load_error);
+  return VKGSB_OK;
+}
+
+int vkgsb_load_ply(vkgsb_renderer* r, const char* path) {
+  if (int e = vkgsb_load_ply_async(r, path)) return e;
+  return vkgsb_wait_load(r);
+}
+
+int vkgsb_load_progress(vkgsb_renderer* r, uint32_t* total, uint32_t* loaded, int* state) {
+  if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
+  if (total) *total = r->total_points.load();
+  if (loaded) *loaded = r->loaded_points.load();
+  if (state) *state = r->load_state.load();
+  return VKGSB_OK;
+}
+
+int vkgsb_cancel_load(vkgsb_renderer* r) {
+  if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
+  r->cancel.store(true);
+  return VKGSB_OK;
+}
+
+int vkgsb_upload_splats(vkgsb_renderer* r, uint32_t n, const float* rows, const uint32_t offsets[60]) {
+  if (!r || !rows || !offsets) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (n == 0) return fail(VKGSB_ERR_INVALID, "n is 0");
+  const uint32_t stride = offsets[59];
+  for (int i = 0; i < 59; ++i)
+    if (offsets[i] >= stride) return fail(VKGSB_ERR_INVALID, "offset table entry beyond the row stride");
+  if (int e = vkgsb_wait_load(r); e != VKGSB_OK && e != VKGSB_ERR_CANCELLED && e != VKGSB_ERR_IO) return e;
+  r->cancel.store(false);
+  int rc = ingest(r, n, stride * 4u, offsets, [&](float* dst, uint64_t first, uint32_t count) {
+    std::memcpy(dst, rows + first * stride, static_cast<size_t>(count) * stride * 4u);
+    return true;
+  });
+  r->load_state.store(rc == VKGSB_OK ? 2 : -rc);
+  return rc;
+}
+
+int vkgsb_set_camera(vkgsb_renderer* r, const vkgsb_camera* cam) {
+  if (!r || !cam) return fail(VKGSB_ERR_INVALID, "null argument");
+  r->cam = *cam;
+  r->have_cam = true;
+  return VKGSB_OK;
+}
+
+int vkgsb_set_viewport(vkgsb_renderer* r, uint32_t width, uint32_t height) {
+  if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
+  if (width == 0 || height == 0) return fail(VKGSB_ERR_INVALID, "empty viewport");
+  if (static_cast<size_t>(width) * height > static_cast<size_t>(r->max_width) * r->max_height ||
+      (width + kTile - 1) / kTile > 1023 || (height + kTile - 1) / kTile > 1023)
+    return fail(VKGSB_ERR_CAPACITY, "viewport larger than the renderer was created for");
+  if (width != r->width || height != r->height) {
+    std::lock_guard<std::mutex> g(r->draw_mutex);
+    r->width = width;
+    r->height = height;
+    invalidate_graph(r);
+  }
+  return VKGSB_OK;
+}
+
+int vkgsb_draw(vkgsb_renderer* r, void* dst, int dst_is_device, void* stream) {
+  if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  std::lock_guard<std::mutex> g(r->draw_mutex);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : r->stream;
+  if (int e = run_frame(r, s)) return e;
+  const size_t bytes = static_cast<size_t>(r->width) * r->height * 4;
+  if (dst) {
+    CU_TRY(cudaMemcpyAsync(dst, r->image, bytes, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    if (!dst_is_device) CU_TRY(cudaStreamSynchronize(s));
+  }
+  return VKGSB_OK;
+}
+
+int vkgsb_draw_batch(vkgsb_renderer* r, uint32_t n_views, const vkgsb_camera* cameras, void* dst, size_t dst_stride,
+                     int dst_is_device, void* stream) {
+  if (!r || !cameras) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  std::lock_guard<std::mutex> g(r->draw_mutex);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : r->stream;
+  const size_t bytes = static_cast<size_t>(r->width) * r->height * 4;
+  if (dst && dst_stride < bytes) return fail(VKGSB_ERR_INVALID, "dst_stride smaller than one image");
+  for (uint32_t i = 0; i < n_views; ++i) {
+    r->cam = cameras[i];
+    r->have_cam = true;
+    if (int e = run_frame(r, s)) return e;
+    if (dst)
+      CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + i * dst_stride, r->image, bytes,
+                             dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  }
+  if (dst && !dst_is_device) CU_TRY(cudaStreamSynchronize(s));
+  return VKGSB_OK;
+}
+
+int vkgsb_image_device_ptr(vkgsb_renderer* r, void** ptr) {
+  if (!r || !ptr) return fail(VKGSB_ERR_INVALID, "null argument");
+  *ptr = r->image;
+  return VKGSB_OK;
+}
+
+int vkgsb_sync(vkgsb_renderer* r) {
+  if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  CU_TRY(cudaStreamSynchronize(r->stream));
+  return VKGSB_OK;
+}
+
+int vkgsb_get_stats(vkgsb_renderer* r, vkgsb_stats* out) {
+  if (!r || !out) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  std::lock_guard<std::mutex> g(r->draw_mutex);
+  CU_TRY(cudaDeviceSynchronize());
+  std::memset(out, 0, sizeof(*out));
+  out->total_point_count = r->total_points.load();
+  out->loaded_point_count = r->loaded_points.load();
+  out->visible_point_count = r->h_counts[0];
+  out->pair_count = r->h_counts[1];
+  out->pair_overflow = r->h_counts[2];
+  out->frame_counter = r->frame_counter;
+  if (r->ev_recorded) {
+    CU_TRY(cudaEventElapsedTime(&out->ms_project, r->ev[0], r->ev[1]));
+    CU_TRY(cudaEventElapsedTime(&out->ms_sort, r->ev[1], r->ev[2]));
+    CU_TRY(cudaEventElapsedTime(&out->ms_bin, r->ev[2], r->ev[3]));
+    CU_TRY(cudaEventElapsedTime(&out->ms_blend, r->ev[3], r->ev[4]));
+    CU_TRY(cudaEventElapsedTime(&out->ms_total, r->ev[0], r->ev[4]));
+  }
+  return VKGSB_OK;
+}
+
+int vkgsb_read_sorted(vkgsb_renderer* r, uint32_t* keys, uint32_t* ids, uint32_t capacity, uint32_t* count) {
+  if (!r || !count) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  std::lock_guard<std::mutex> g(r->draw_mutex);
+  CU_TRY(cudaDeviceSynchronize());
+  uint32_t v = 0;
+  CU_TRY(cudaMemcpy(&v, &r->ctrl->visible_count, 4, cudaMemcpyDeviceToHost));
+  *count = v;
+  if (v > capacity) return fail(VKGSB_ERR_CAPACITY, "capacity smaller than the visible count");
+  if (v == 0) return VKGSB_OK;
+  if (keys) CU_TRY(cudaMemcpy(keys, r->keys, v * 4ull, cudaMemcpyDeviceToHost));
+  if (ids) {
+    // slots_alt is free between frames: gather ids there
+    launch_gather_sorted(r->ctrl, r->slots, r->vis_id, r->inst, v, r->slots_alt, nullptr, r->stream);
+    CU_TRY(cudaStreamSynchronize(r->stream));
+    CU_TRY(cudaMemcpy(ids, r->slots_alt, v * 4ull, cudaMemcpyDeviceToHost));
+  }
+  return VKGSB_OK;
+}
+
+int vkgsb_read_instances(vkgsb_renderer* r, float* inst, uint32_t capacity, uint32_t* count) {
+  if (!r || !count) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  std::lock_guard<std::mutex> g(r->draw_mutex);
+  CU_TRY(cudaDeviceSynchronize());
+  uint32_t v = 0;
+  CU_TRY(cudaMemcpy(&v, &r->ctrl->visible_count, 4, cudaMemcpyDeviceToHost));
+  *count = v;
+  if (v > capacity) return fail(VKGSB_ERR_CAPACITY, "capacity smaller than the visible count");
+  if (v == 0 || !inst) return VKGSB_OK;
+  float* tmp = nullptr;
+  CU_TRY(cudaMalloc(&tmp, v * 48ull));
+  launch_gather_sorted(r->ctrl, r->slots, r->vis_id, r->inst, v, nullptr, tmp, r->stream);
+  cudaError_t e = cudaStreamSynchronize(r->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(inst, tmp, v * 48ull, cudaMemcpyDeviceToHost);
+  cudaFree(tmp);
+  CU_TRY(e);
+  return VKGSB_OK;
+}
+
+int vkgsb_read_scene(vkgsb_renderer* r, float* pos, float* cov, float* opacity, uint16_t* sh, uint32_t capacity,
+                     uint32_t* count) {
+  if (!r || !count) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  const uint32_t n = r->scene_n.load();
+  *count = n;
+  if (n > capacity) return fail(VKGSB_ERR_CAPACITY, "capacity smaller than the scene");
+  if (n == 0) return VKGSB_OK;
+  float *dp = nullptr, *dc = nullptr, *dop = nullptr;
+  uint16_t* ds = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (pos && e == cudaSuccess) e = cudaMalloc(&dp, n * 12ull);
+  if (cov && e == cudaSuccess) e = cudaMalloc(&dc, n * 24ull);
+  if (opacity && e == cudaSuccess) e = cudaMalloc(&dop, n * 4ull);
+  if (sh && e == cudaSuccess) e = cudaMalloc(&ds, n * 96ull);
+  if (e == cudaSuccess) {
+    launch_export_scene(r->scene, n, dp, dc, dop, ds, r->stream);
+    e = cudaStreamSynchronize(r->stream);
+  }
+  if (pos && e == cudaSuccess) e = cudaMemcpy(pos, dp, n * 12ull, cudaMemcpyDeviceToHost);
+  if (cov && e == cudaSuccess) e = cudaMemcpy(cov, dc, n * 24ull, cudaMemcpyDeviceToHost);
+  if (opacity && e == cudaSuccess) e = cudaMemcpy(opacity, dop, n * 4ull, cudaMemcpyDeviceToHost);
+  if (sh && e == cudaSuccess) e = cudaMemcpy(sh, ds, n * 96ull, cudaMemcpyDeviceToHost);
+  cudaFree(dp); cudaFree(dc); cudaFree(dop); cudaFree(ds);
+  CU_TRY(e);
+  return VKGSB_OK;
+}
+
+// ---- stage-level sort plug-in (vrdx* surface) -----------------------------------------------------------------------
+// storage layout: [hist 4x256 u32][tickets 4 u32 (+pad)][look-back 4 x parts x 256 u32][keys_alt max_n][vals_alt max_n]
+static size_t sort_storage_layout(uint32_t max_n, size_t* off_lookback, size_t* off_keys, size_t* off_vals) {
+  size_t o = 4 * 256 * 4 + 64;
+  *off_lookback = o;
+  o += sort_lookback_bytes(max_n, 4);
+  o = (o + 255) & ~size_t(255);
+  *off_keys = o;
+  o += (static_cast<size_t>(max_n) * 4 + 255) & ~size_t(255);
+  *off_vals = o;
+  o += (static_cast<size_t>(max_n) * 4 + 255) & ~size_t(255);
+  return o;
+}
+
+int vkgsb_sort_storage_bytes(uint32_t max_element_count, size_t* bytes) {
+  if (!bytes) return fail(VKGSB_ERR_INVALID, "bytes is null");
+  size_t a, b, c;
+  *bytes = sort_storage_layout(max_element_count, &a, &b, &c);
+  return VKGSB_OK;
+}
+
+int vkgsb_sort_key_value_indirect(void* stream, uint32_t max_element_count, const uint32_t* d_count, uint32_t* d_keys,
+                                  uint32_t* d_values, void* d_storage) {
+  if (!d_count || !d_keys || !d_values || !d_storage) return fail(VKGSB_ERR_INVALID, "null device pointer");
+  if (max_element_count == 0) return VKGSB_OK;
+  if (max_element_count > (1u << 30)) return fail(VKGSB_ERR_CAPACITY, "at most 2^30 elements");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  size_t off_lb, off_k, off_v;
+  sort_storage_layout(max_element_count, &off_lb, &off_k, &off_v);
+  uint8_t* base = static_cast<uint8_t*>(d_storage);
+  CU_TRY(cudaMemsetAsync(base, 0, 4 * 256 * 4 + 64, s));
+  SortArgs a{};
+  a.d_count = d_count;
+  a.max_n = max_element_count;
+  a.keys = d_keys; a.vals = d_values;
+  a.keys_alt = reinterpret_cast<uint32_t*>(base + off_k);
+  a.vals_alt = reinterpret_cast<uint32_t*>(base + off_v);
+  a.hist = reinterpret_cast<uint32_t*>(base);
+  a.tickets = reinterpret_cast<uint32_t*>(base + 4 * 256 * 4);
+  a.lookback = reinterpret_cast<uint32_t*>(base + off_lb);
+  a.begin_bit = 0;
+  a.npass = 4;
+  launch_sort(a, s);
+  CU_TRY(cudaGetLastError());
+  return VKGSB_OK;
+}
+
+}  // extern "C"
