@@ -133,6 +133,15 @@ def raster(inst: np.ndarray, width: int, height: int, mode: int = 0, tile: int =
     return (out, fout) if want_float else out
 
 
+def raster_rows(inst: np.ndarray, width: int, height: int, row0: int, row1: int, mode: int = 0, tile: int = 16):
+    """Only tile bands overlapping rows [row0,row1) are rasterised (bounded CPU sample for bench.py)."""
+    inst = _f32(inst).reshape(-1, 12)
+    out = np.zeros((height, width, 4), np.uint8)
+    lib().vko_raster_rows(C.c_uint32(inst.shape[0]), _p(inst), C.c_uint32(width), C.c_uint32(height), C.c_uint32(tile),
+                          C.c_int(mode), C.c_uint32(row0), C.c_uint32(row1), _p(out), None)
+    return out
+
+
 def render(scene: Scene, cam: Camera, mode: int = 0, tile: int = 16):
     """Whole frame; returns dict(image, keys, ids, inst, stats)."""
     keys = np.empty(scene.n, np.uint32); ids = np.empty(scene.n, np.uint32)

@@ -423,15 +423,18 @@ static inline uint8_t q8(float x) {
   return (uint8_t)v;
 }
 
-VKO_API void vko_raster(uint32_t v, const float* inst, uint32_t W, uint32_t H, uint32_t tile, int mode,
-                        uint8_t* out, float* fout) {
+/* Rows outside [row0,row1) (rounded outwards to whole tile bands) are left untouched in out. */
+VKO_API void vko_raster_rows(uint32_t v, const float* inst, uint32_t W, uint32_t H, uint32_t tile, int mode,
+                             uint32_t row0, uint32_t row1, uint8_t* out, float* fout) {
   raster_splat* S = (raster_splat*)malloc((size_t)(v ? v : 1) * sizeof(raster_splat));
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)v; ++i) raster_setup(inst + 12 * i, W, H, &S[i]);
 
   int nband = (int)((H + tile - 1) / tile);
+  int band_lo = (int)(row0 / tile), band_hi = (int)((row1 + tile - 1) / tile);
+  if (band_hi > nband) band_hi = nband;
 #pragma omp parallel for schedule(dynamic, 1)
-  for (int band = 0; band < nband; ++band) {
+  for (int band = band_lo; band < band_hi; ++band) {
     int by0 = band * (int)tile, by1 = by0 + (int)tile - 1;
     if (by1 > (int)H - 1) by1 = (int)H - 1;
     size_t npx = (size_t)W * (size_t)(by1 - by0 + 1);
@@ -495,6 +498,11 @@ VKO_API void vko_raster(uint32_t v, const float* inst, uint32_t W, uint32_t H, u
     free(acc);
   }
   free(S);
+}
+
+VKO_API void vko_raster(uint32_t v, const float* inst, uint32_t W, uint32_t H, uint32_t tile, int mode,
+                        uint8_t* out, float* fout) {
+  vko_raster_rows(v, inst, W, H, tile, mode, 0, H, out, fout);
 }
 
 /* ------------------------------------------------------------ whole frame */

@@ -698,8 +698,8 @@ int vkgsb_sort_storage_bytes(uint32_t max_element_count, size_t* bytes) {
 
 int vkgsb_sort_key_value_indirect(void* stream, uint32_t max_element_count, const uint32_t* d_count, uint32_t* d_keys,
                                   uint32_t* d_values, void* d_storage) {
+  if (max_element_count == 0) return VKGSB_OK;  // nothing to sort; pointers are not inspected
   if (!d_count || !d_keys || !d_values || !d_storage) return fail(VKGSB_ERR_INVALID, "null device pointer");
-  if (max_element_count == 0) return VKGSB_OK;
   if (max_element_count > (1u << 30)) return fail(VKGSB_ERR_CAPACITY, "at most 2^30 elements");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   size_t off_lb, off_k, off_v;

@@ -1,0 +1,78 @@
+"""Multi-GPU host logic.  The reference is single-GPU; the path shards two ways, both with the
+scene replicated per GPU and no collective on the data path except gathering finished pixels:
+
+  by view   cameras dealt to ranks in contiguous blocks; every rank runs the whole frame pipeline per view;
+            images are gathered to one rank (NCCL on GPUs, gloo in the CPU tests).
+  by band   one view, rank g bins and blends only rows [edge[g], edge[g+1]) (VKGSB_OPT_BAND_Y0/Y1); the cull and the
+            depth sort are replicated so every band sees the same global order; bands concatenate to the frame.
+
+Everything here is plumbing around torch.distributed; it never touches pixels' values.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_views(n_views: int, rank: int, world: int) -> range:
+    """Contiguous block of view indices for `rank` (blocks differ by at most one view)."""
+    base, extra = divmod(n_views, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def band_edges(height: int, world: int, align: int = 16) -> List[int]:
+    """Row boundaries of `world` horizontal bands, tile-aligned where possible, covering [0, height)."""
+    tiles = (height + align - 1) // align
+    edges = [min(height, ((tiles * g) // world) * align) for g in range(world)] + [height]
+    return edges
+
+
+def gather_images(local, dst: int = 0, group=None):
+    """Gather equally shaped uint8 image tensors [B,H,W,4] to rank `dst`.  Returns the list on dst, else None."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return [local]
+    rank = dist.get_rank(group)
+    if dist.get_backend(group) == "nccl":
+        # NCCL has no native gather in older torch builds for uint8 lists; all ranks send, dst receives
+        import torch
+        outs = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
+        dist.gather(local, outs, dst=dst, group=group)
+        return outs
+    import torch
+    outs = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
+    dist.gather(local, outs, dst=dst, group=group)
+    return outs
+
+
+def assemble_views(gathered: Sequence, n_views: int) -> "np.ndarray":
+    """Inverse of shard_views: per-rank [b_r,H,W,4] blocks -> [n_views,H,W,4] in view order."""
+    import torch
+    world = len(gathered)
+    parts = []
+    for r in range(world):
+        k = len(shard_views(n_views, r, world))
+        parts.append(gathered[r][:k])
+    return torch.cat(parts, dim=0)
+
+
+def assemble_bands(gathered: Sequence, edges: Sequence[int]):
+    """Per-rank full-size frames whose own band rows are valid -> one frame."""
+    import torch
+    out = torch.empty_like(gathered[0])
+    for g, img in enumerate(gathered):
+        out[..., edges[g]:edges[g + 1], :, :] = img[..., edges[g]:edges[g + 1], :, :]
+    return out
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
