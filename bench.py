@@ -193,13 +193,16 @@ def main():
 
     K, W = args.steps, args.warmup
     rows = synth.scene_bicycle(N_SPLATS)
-    r = vkgs_b200.Renderer(device=local, max_splats=N_SPLATS, max_width=WIDTH, max_height=HEIGHT, max_pairs=160_000_000)
+    r = vkgs_b200.Renderer(device=local, max_splats=N_SPLATS, max_width=WIDTH, max_height=HEIGHT, max_pairs=64_000_000)
     r.upload_splats(rows)
     del rows
     r.set_viewport(WIDTH, HEIGHT)
     r.set_blend_mode(L.BLEND_UNORM8 if args.blend == "unorm8" else L.BLEND_FP32)
-    stream = torch.cuda.current_stream()
+    # a side stream: the legacy default stream's handle is 0, which the C ABI reads as "the renderer's own stream"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
     cams = [vkgs_b200.camera_block(*view_camera(rank * K + i)) for i in range(max(K, W))]
     img_bytes = WIDTH * HEIGHT * 4
     GATHER_EVERY = 4

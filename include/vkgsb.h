@@ -62,7 +62,7 @@ typedef struct vkgsb_config {
                            0 => 1<<23 */
   uint32_t max_width;   /* 0 => 3840 */
   uint32_t max_height;  /* 0 => 2160 */
-  uint64_t max_pairs;   /* capacity of the (tile, splat) binning list; 0 => 16 * max_splats */
+  uint64_t max_pairs;   /* capacity of the (bin, splat) binning list; 0 => 8 * max_splats */
 } vkgsb_config;
 
 /* The per-frame parameter block: shader::Camera (uniforms.h:10-15) + the `mat4 model` push constant
@@ -81,7 +81,7 @@ typedef struct vkgsb_stats {
   uint32_t loaded_point_count;
   uint32_t visible_point_count; /* V of the last drawn frame */
   uint32_t pair_overflow;       /* 1 if the binning list hit max_pairs (farthest splats were dropped) */
-  uint64_t pair_count;          /* (tile, splat) pairs of the last frame */
+  uint64_t pair_count;          /* (bin, splat) pairs of the last frame */
   float ms_project;             /* rank.comp + projection.comp equivalent */
   float ms_sort;                /* vrdxCmdSortKeyValueIndirect equivalent */
   float ms_bin;                 /* tile binning (no reference equivalent: replaces the HW rasteriser's setup) */

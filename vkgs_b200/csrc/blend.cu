@@ -3,14 +3,18 @@
 // SRC_ALPHA / ONE_MINUS_SRC_ALPHA for colour AND alpha (engine.cc:281-289), clear (0,0,0,1) (engine.cc:1382-1387),
 // depth LESS / no write (graphics_pipeline.cc:79-81; applied in bin.cu), B8G8R8A8_UNORM target (render_pass.cc:15).
 //
-// One CTA per 16x16 tile walks the tile's nearest-first splat list in batches staged through shared memory.
-// Per-fragment arithmetic is the pinned form shared with oracle/vkgs_oracle.c (tile-origin-relative):
+// One 1024-thread CTA per 64x64-pixel bin streams the bin's nearest-first splat list in batches of 1024 through
+// shared memory.  While staging, each thread turns its splat's pixel bounding box into a 32-bit mask over the bin's
+// 4x8 sub-tiles (16x8 pixels, one per warp); each warp then picks its splats out of the batch with one ballot per
+// 32 entries and shades them, 4 pixels per lane.  So a splat only costs the warps it can touch, and a warp whose 128
+// pixels are all saturated drops out of the masks; the CTA stops when every warp has.
+// Per-fragment arithmetic is the pinned form shared with oracle/vkgs_oracle.c (16-pixel-tile-origin-relative):
 //   px = fma(A00, lx, fma(A01, ly, bx)),  py = fma(A10, lx, fma(A11, ly, by)),  covered <=> |px|<=3 && |py|<=3
-// with A = (diag(W/2,H/2) * RS)^-1 and b = A * (tile_origin - centre_px) built from non-fused mul/add.
+// with A = (diag(W/2,H/2) * RS)^-1 (bin.cu) and b = A * (tile_origin - centre_px) from non-fused mul/add.
 //
-// VKGSB_BLEND_FP32   front-to-back: C += c*a*T, A += a*a*T, T *= 1-a; a pixel retires at T < 1e-4, a tile when all
-//                    its pixels have.  Exact-arithmetic identical to the reference's back-to-front recurrence
-//                    (C <- c*a + C*(1-a), A <- a*a + A*(1-a), A0 = 1); one UNORM8 rounding at the end.
+// VKGSB_BLEND_FP32   front-to-back: C += c*a*T, A += a*a*T, T *= 1-a; a pixel retires at T < 1e-4.  In exact
+//                    arithmetic identical to the reference's back-to-front recurrence (C <- c*a + C*(1-a),
+//                    A <- a*a + A*(1-a), A0 = 1); one UNORM8 rounding at the end.
 // VKGSB_BLEND_UNORM8 back-to-front, destination re-quantised after every splat like an 8-bit ROP:
 //                    q <- rint(fma(255*src, a, q*(1-a))); no early exit possible.
 #include "common.cuh"
@@ -18,147 +22,206 @@
 
 namespace vkgsb {
 
-constexpr int kBlendThreads = kTile * kTile;  // one pixel per thread
-constexpr int kBatch = 256;
+constexpr int kBlendThreads = 1024;
+constexpr int kBatch = 1024;
+constexpr int kPix = 4;  // pixels per lane: rows ly0 + 2k of a 16x8 sub-tile
 constexpr float kTransmittanceCut = 1e-4f;
-
-struct __align__(16) Staged {
-  float a00, a01, a10, a11;
-  float bx, by, r, g;
-  float b, op, pad0, pad1;
-};
-
-// Per (tile, splat) setup from the 12-float instance record; mirrors raster_setup() + the tile terms in the oracle.
-__device__ __forceinline__ Staged stage_splat(const float4 r0, const float4 r1, const float4 r2, float hw, float hh,
-                                              float tile_x, float tile_y) {
-  Staged s;
-  const float cpx = fmaf(r0.x, hw, hw - 0.5f), cpy = fmaf(r0.y, hh, hh - 0.5f);
-  const float m00 = __fmul_rn(r1.x, hw), m10 = __fmul_rn(r1.y, hh), m01 = __fmul_rn(r1.z, hw), m11 = __fmul_rn(r1.w, hh);
-  const float det = __fsub_rn(__fmul_rn(m00, m11), __fmul_rn(m01, m10));
-  s.a00 = __fdiv_rn(m11, det);
-  s.a01 = __fdiv_rn(-m01, det);
-  s.a10 = __fdiv_rn(-m10, det);
-  s.a11 = __fdiv_rn(m00, det);
-  const float ox = __fsub_rn(tile_x, cpx), oy = __fsub_rn(tile_y, cpy);
-  s.bx = __fadd_rn(__fmul_rn(s.a00, ox), __fmul_rn(s.a01, oy));
-  s.by = __fadd_rn(__fmul_rn(s.a10, ox), __fmul_rn(s.a11, oy));
-  s.r = __saturatef(r2.x);  // source colour is clamped by the UNORM target; NaN -> 0
-  s.g = __saturatef(r2.y);
-  s.b = __saturatef(r2.z);
-  s.op = r2.w;
-  s.pad0 = s.pad1 = 0.f;
-  return s;
-}
+constexpr size_t kBlendSmem = kBatch * (3 * sizeof(float4) + sizeof(uint32_t));
 
 __device__ __forceinline__ uint32_t quantize8(float x) {  // RNE, saturating
   return static_cast<uint32_t>(__float2int_rn(__saturatef(x) * 255.f));
 }
+__device__ __forceinline__ uint32_t clamp255(float q) { return static_cast<uint32_t>(fminf(fmaxf(q, 0.f), 255.f)); }
 
-__device__ __forceinline__ void store_pixel(uint8_t* image, uint32_t width, uint32_t x, uint32_t y, uint32_t r, uint32_t g,
-                                            uint32_t b, uint32_t a, int bgra) {
-  const uint32_t w = bgra ? (b | (g << 8) | (r << 16) | (a << 24)) : (r | (g << 8) | (b << 16) | (a << 24));
-  reinterpret_cast<uint32_t*>(image)[static_cast<size_t>(y) * width + x] = w;
+__device__ __forceinline__ uint32_t pack_pixel(uint32_t r, uint32_t g, uint32_t b, uint32_t a, int bgra) {
+  return bgra ? (b | (g << 8) | (r << 16) | (a << 24)) : (r | (g << 8) | (b << 16) | (a << 24));
+}
+
+// 32-bit mask (bit = row * 4 + col) of the bin's sub-tiles a pixel box [x0,x1] x [y0,y1] touches.
+__device__ __forceinline__ uint32_t subtile_mask(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, uint32_t bin_x,
+                                                 uint32_t bin_y) {
+  const int c0 = max(static_cast<int>(x0) - static_cast<int>(bin_x), 0) / kSubW;
+  const int c1 = min(static_cast<int>(x1) - static_cast<int>(bin_x), kBinW - 1) / kSubW;
+  const int r0 = max(static_cast<int>(y0) - static_cast<int>(bin_y), 0) / kSubH;
+  const int r1 = min(static_cast<int>(y1) - static_cast<int>(bin_y), kBinH - 1) / kSubH;
+  if (c1 < c0 || r1 < r0) return 0u;
+  const uint32_t cols = ((1u << (c1 - c0 + 1)) - 1u) << c0;                                       // 4 bits
+  const uint32_t rows = static_cast<uint32_t>(((1ull << (4 * (r1 + 1))) - (1ull << (4 * r0)))) & 0x11111111u;
+  return rows * cols;  // no carries: cols <= 0xF
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kBlendThreads)
-k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ pair_slot,
-        const float4* __restrict__ inst, int bgra, uint8_t* __restrict__ image) {
-  __shared__ Staged s_splat[kBatch];
+__global__ void __launch_bounds__(kBlendThreads, 1)
+k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ pair_rank,
+        const float4* __restrict__ rrec, int bgra, uint8_t* __restrict__ image) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float4* s_q0 = reinterpret_cast<float4*>(smem_raw);
+  float4* s_q1 = s_q0 + kBatch;
+  float4* s_q2 = s_q1 + kBatch;
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_q2 + kBatch);
+  __shared__ uint32_t s_alive;
 
-  const uint32_t width = fpp->width, height = fpp->height, tiles_x = fpp->tiles_x;
-  const uint32_t band_y0 = fpp->band_y0, band_y1 = fpp->band_y1, tile_y0 = fpp->tile_y0;
-  const uint32_t tile = blockIdx.x, tx = tile % tiles_x, ty = tile / tiles_x + tile_y0;
-  const uint32_t tid = threadIdx.x, lx = tid % kTile, ly = tid / kTile;
-  const uint32_t x = tx * kTile + lx, y = ty * kTile + ly;
-  const bool inside = x < width && y >= band_y0 && y < band_y1 && y < height;
-  const float hw = 0.5f * static_cast<float>(width), hh = 0.5f * static_cast<float>(height);
-  const float tile_x = static_cast<float>(tx * kTile), tile_y = static_cast<float>(ty * kTile);
-  const float flx = static_cast<float>(lx), fly = static_cast<float>(ly);
-  const uint2 range = ranges[tile];
+  const uint32_t width = fpp->width, bins_x = fpp->bins_x;
+  const uint32_t band_y0 = fpp->band_y0, band_y1 = fpp->band_y1;
+  const uint32_t bin = blockIdx.x, bin_x = (bin % bins_x) * kBinW, bin_y = (bin / bins_x + fpp->bin_y0) * kBinH;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t sub_x = bin_x + (warp % kSubCols) * kSubW, sub_y = bin_y + (warp / kSubCols) * kSubH;
+  const uint32_t x = sub_x + (lane & 15u), y_first = sub_y + (lane >> 4);
+  const uint32_t org_y = sub_y & ~static_cast<uint32_t>(kTile - 1);  // 16-aligned origin (sub_x already is)
+  const float tile_x = static_cast<float>(sub_x), tile_y = static_cast<float>(org_y);
+  const float flx = static_cast<float>(lane & 15u);
+  float fly[kPix];
+  bool inside[kPix];
+#pragma unroll
+  for (int k = 0; k < kPix; ++k) {
+    const uint32_t y = y_first + 2 * k;
+    fly[k] = static_cast<float>(y - org_y);
+    inside[k] = x < width && y >= band_y0 && y < band_y1;
+  }
+  const uint2 range = ranges[bin];
+  const uint32_t wbit = 1u << warp;
 
   if (MODE == VKGSB_BLEND_FP32_MODE) {
-    float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, ca = 0.f;
-    bool done = !inside;
+    float T[kPix], cr[kPix], cg[kPix], cb[kPix], ca[kPix];
+    bool done[kPix];
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) {
+      T[k] = 1.f; cr[k] = cg[k] = cb[k] = ca[k] = 0.f;
+      done[k] = !inside[k];
+    }
+    bool warp_done = __all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3]);
+    if (tid == 0) s_alive = 0xffffffffu;
+    __syncthreads();
+    if (warp_done && lane == 0) atomicAnd(&s_alive, ~wbit);
+    __syncthreads();
+
     for (uint32_t b0 = range.x; b0 < range.y; b0 += kBatch) {
-      if (__syncthreads_and(done)) break;
+      const uint32_t alive = s_alive;
+      if (alive == 0u) break;
       const uint32_t cnt = min(static_cast<uint32_t>(kBatch), range.y - b0);
       if (tid < cnt) {
-        const uint32_t slot = __ldg(pair_slot + b0 + tid);
-        s_splat[tid] = stage_splat(__ldg(inst + slot * 3 + 0), __ldg(inst + slot * 3 + 1), __ldg(inst + slot * 3 + 2), hw,
-                                   hh, tile_x, tile_y);
+        const uint32_t rank = __ldg(pair_rank + b0 + tid);
+        const float4 q0 = __ldg(rrec + rank * 3 + 0), q1 = __ldg(rrec + rank * 3 + 1), q2 = __ldg(rrec + rank * 3 + 2);
+        const uint32_t bxw = __float_as_uint(q2.z), byw = __float_as_uint(q2.w);
+        s_q0[tid] = q0; s_q1[tid] = q1; s_q2[tid] = q2;
+        s_mask[tid] = subtile_mask(bxw & 0xffffu, bxw >> 16, byw & 0xffffu, byw >> 16, bin_x, bin_y) & alive;
       }
       __syncthreads();
-      if (!done) {
-        for (uint32_t j = 0; j < cnt; ++j) {
-          const Staged s = s_splat[j];
-          const float px = fmaf(s.a00, flx, fmaf(s.a01, fly, s.bx));
-          const float py = fmaf(s.a10, flx, fmaf(s.a11, fly, s.by));
-          if (!(fabsf(px) <= 3.f && fabsf(py) <= 3.f)) continue;
-          float al = s.op * __expf(-0.5f * fmaf(py, py, px * px));
-          al = __saturatef(al);
-          const float w = al * T;
-          cr = fmaf(s.r, w, cr);
-          cg = fmaf(s.g, w, cg);
-          cb = fmaf(s.b, w, cb);
-          ca = fmaf(al, w, ca);
-          T -= w;
-          if (T < kTransmittanceCut) {
-            done = true;
-            break;
+      if (!warp_done) {
+        for (uint32_t g0 = 0; g0 < cnt && !warp_done; g0 += 32) {
+          const uint32_t m = (g0 + lane < cnt) ? s_mask[g0 + lane] : 0u;
+          uint32_t bits = __ballot_sync(0xffffffffu, (m & wbit) != 0u);
+          while (bits) {
+            const uint32_t j = g0 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            const float4 q0 = s_q0[j], q1 = s_q1[j];
+            const float2 q2 = *reinterpret_cast<const float2*>(&s_q2[j]);
+            const float ox = __fsub_rn(tile_x, q1.x), oy = __fsub_rn(tile_y, q1.y);
+            const float bx = __fadd_rn(__fmul_rn(q0.x, ox), __fmul_rn(q0.y, oy));
+            const float by = __fadd_rn(__fmul_rn(q0.z, ox), __fmul_rn(q0.w, oy));
+#pragma unroll
+            for (int k = 0; k < kPix; ++k) {
+              const float px = fmaf(q0.x, flx, fmaf(q0.y, fly[k], bx));
+              const float py = fmaf(q0.z, flx, fmaf(q0.w, fly[k], by));
+              if (!done[k] && fabsf(px) <= 3.f && fabsf(py) <= 3.f) {
+                const float al = __saturatef(q2.y * __expf(-0.5f * fmaf(py, py, px * px)));
+                const float w = al * T[k];
+                cr[k] = fmaf(q1.z, w, cr[k]);
+                cg[k] = fmaf(q1.w, w, cg[k]);
+                cb[k] = fmaf(q2.x, w, cb[k]);
+                ca[k] = fmaf(al, w, ca[k]);
+                T[k] -= w;
+                done[k] = T[k] < kTransmittanceCut;
+              }
+            }
+            if (__all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3])) {
+              warp_done = true;
+              if (lane == 0) atomicAnd(&s_alive, ~wbit);
+              break;
+            }
           }
         }
       }
+      __syncthreads();
     }
-    if (inside) store_pixel(image, width, x, y, quantize8(cr), quantize8(cg), quantize8(cb), quantize8(ca + T), bgra);
+    uint32_t* img = reinterpret_cast<uint32_t*>(image);
+#pragma unroll
+    for (int k = 0; k < kPix; ++k)
+      if (inside[k])
+        img[static_cast<size_t>(y_first + 2 * k) * width + x] =
+            pack_pixel(quantize8(cr[k]), quantize8(cg[k]), quantize8(cb[k]), quantize8(ca[k] + T[k]), bgra);
   } else {
     // back-to-front over the nearest-first list: batches from the tail, entries in reverse
-    float qr = 0.f, qg = 0.f, qb = 0.f, qa = 255.f;
+    float qr[kPix], qg[kPix], qb[kPix], qa[kPix];
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) { qr[k] = qg[k] = qb[k] = 0.f; qa[k] = 255.f; }
     uint32_t remaining = range.y - range.x;
     while (remaining > 0) {
       const uint32_t cnt = min(static_cast<uint32_t>(kBatch), remaining);
       const uint32_t b0 = range.x + remaining - cnt;
       __syncthreads();
       if (tid < cnt) {
-        const uint32_t slot = __ldg(pair_slot + b0 + tid);
-        s_splat[tid] = stage_splat(__ldg(inst + slot * 3 + 0), __ldg(inst + slot * 3 + 1), __ldg(inst + slot * 3 + 2), hw,
-                                   hh, tile_x, tile_y);
+        const uint32_t rank = __ldg(pair_rank + b0 + tid);
+        const float4 q0 = __ldg(rrec + rank * 3 + 0), q1 = __ldg(rrec + rank * 3 + 1), q2 = __ldg(rrec + rank * 3 + 2);
+        const uint32_t bxw = __float_as_uint(q2.z), byw = __float_as_uint(q2.w);
+        s_q0[tid] = q0; s_q1[tid] = q1; s_q2[tid] = q2;
+        s_mask[tid] = subtile_mask(bxw & 0xffffu, bxw >> 16, byw & 0xffffu, byw >> 16, bin_x, bin_y);
       }
       __syncthreads();
-      if (inside) {
-        for (int j = static_cast<int>(cnt) - 1; j >= 0; --j) {
-          const Staged s = s_splat[j];
-          const float px = fmaf(s.a00, flx, fmaf(s.a01, fly, s.bx));
-          const float py = fmaf(s.a10, flx, fmaf(s.a11, fly, s.by));
-          if (!(fabsf(px) <= 3.f && fabsf(py) <= 3.f)) continue;
-          float al = s.op * __expf(-0.5f * fmaf(py, py, px * px));
-          al = __saturatef(al);
-          const float om = __fsub_rn(1.f, al);
-          qr = rintf(fmaf(__fmul_rn(255.f, s.r), al, __fmul_rn(qr, om)));
-          qg = rintf(fmaf(__fmul_rn(255.f, s.g), al, __fmul_rn(qg, om)));
-          qb = rintf(fmaf(__fmul_rn(255.f, s.b), al, __fmul_rn(qb, om)));
-          qa = rintf(fmaf(__fmul_rn(255.f, al), al, __fmul_rn(qa, om)));
+      for (int g0 = static_cast<int>((cnt - 1) & ~31u); g0 >= 0; g0 -= 32) {
+        const uint32_t m = (g0 + lane < cnt) ? s_mask[g0 + lane] : 0u;
+        uint32_t bits = __ballot_sync(0xffffffffu, (m & wbit) != 0u);
+        while (bits) {
+          const uint32_t top = 31u - __clz(bits);
+          const uint32_t j = g0 + top;
+          bits &= ~(1u << top);
+          const float4 q0 = s_q0[j], q1 = s_q1[j];
+          const float2 q2 = *reinterpret_cast<const float2*>(&s_q2[j]);
+          const float ox = __fsub_rn(tile_x, q1.x), oy = __fsub_rn(tile_y, q1.y);
+          const float bx = __fadd_rn(__fmul_rn(q0.x, ox), __fmul_rn(q0.y, oy));
+          const float by = __fadd_rn(__fmul_rn(q0.z, ox), __fmul_rn(q0.w, oy));
+          const float r255 = __fmul_rn(255.f, q1.z), g255 = __fmul_rn(255.f, q1.w), b255 = __fmul_rn(255.f, q2.x);
+#pragma unroll
+          for (int k = 0; k < kPix; ++k) {
+            const float px = fmaf(q0.x, flx, fmaf(q0.y, fly[k], bx));
+            const float py = fmaf(q0.z, flx, fmaf(q0.w, fly[k], by));
+            if (fabsf(px) <= 3.f && fabsf(py) <= 3.f) {
+              const float al = __saturatef(q2.y * __expf(-0.5f * fmaf(py, py, px * px)));
+              const float om = __fsub_rn(1.f, al);
+              qr[k] = rintf(fmaf(r255, al, __fmul_rn(qr[k], om)));
+              qg[k] = rintf(fmaf(g255, al, __fmul_rn(qg[k], om)));
+              qb[k] = rintf(fmaf(b255, al, __fmul_rn(qb[k], om)));
+              qa[k] = rintf(fmaf(__fmul_rn(255.f, al), al, __fmul_rn(qa[k], om)));
+            }
+          }
         }
       }
       remaining -= cnt;
     }
-    if (inside)
-      store_pixel(image, width, x, y, static_cast<uint32_t>(fminf(fmaxf(qr, 0.f), 255.f)),
-                  static_cast<uint32_t>(fminf(fmaxf(qg, 0.f), 255.f)), static_cast<uint32_t>(fminf(fmaxf(qb, 0.f), 255.f)),
-                  static_cast<uint32_t>(fminf(fmaxf(qa, 0.f), 255.f)), bgra);
+    uint32_t* img = reinterpret_cast<uint32_t*>(image);
+#pragma unroll
+    for (int k = 0; k < kPix; ++k)
+      if (inside[k])
+        img[static_cast<size_t>(y_first + 2 * k) * width + x] =
+            pack_pixel(clamp255(qr[k]), clamp255(qg[k]), clamp255(qb[k]), clamp255(qa[k]), bgra);
   }
 }
 
-void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_slot,
-                  const float* d_inst, int blend_mode, int bgra, uint8_t* d_image, cudaStream_t stream) {
-  const uint32_t ntiles = h_fp.tiles_x * (h_fp.tile_y1 - h_fp.tile_y0);
-  if (ntiles == 0) return;
-  if (blend_mode == 0)
-    k_blend<VKGSB_BLEND_FP32_MODE><<<ntiles, kBlendThreads, 0, stream>>>(d_fp, d_ranges, d_pair_slot,
-                                                                       reinterpret_cast<const float4*>(d_inst), bgra, d_image);
+void blend_configure() {
+  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_FP32_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmem);
+  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_UNORM8_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmem);
+}
+
+void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_rank,
+                  const float* d_rrec, int blend_mode, int bgra, uint8_t* d_image, cudaStream_t stream) {
+  const uint32_t nbins = h_fp.bins_x * (h_fp.bin_y1 - h_fp.bin_y0);
+  if (nbins == 0) return;
+  if (blend_mode == VKGSB_BLEND_FP32_MODE)
+    k_blend<VKGSB_BLEND_FP32_MODE><<<nbins, kBlendThreads, kBlendSmem, stream>>>(
+        d_fp, d_ranges, d_pair_rank, reinterpret_cast<const float4*>(d_rrec), bgra, d_image);
   else
-    k_blend<VKGSB_BLEND_UNORM8_MODE><<<ntiles, kBlendThreads, 0, stream>>>(d_fp, d_ranges, d_pair_slot,
-                                                                         reinterpret_cast<const float4*>(d_inst), bgra, d_image);
+    k_blend<VKGSB_BLEND_UNORM8_MODE><<<nbins, kBlendThreads, kBlendSmem, stream>>>(
+        d_fp, d_ranges, d_pair_rank, reinterpret_cast<const float4*>(d_rrec), bgra, d_image);
 }
 
 }  // namespace vkgsb

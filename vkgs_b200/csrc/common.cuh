@@ -7,7 +7,12 @@
 
 namespace vkgsb {
 
-constexpr int kTile = 16;              // blend tile edge in pixels (also the origin of the pinned fragment arithmetic)
+constexpr int kTile = 16;              // origin granularity of the pinned fragment arithmetic (oracle: TILE = 16)
+// Binning granularity: one CTA of the blend stage owns a kBinW x kBinH pixel bin and splits it into 32 sub-tiles of
+// kSubW x kSubH pixels, one per warp (4 pixels per lane).
+constexpr int kBinW = 64, kBinH = 64, kSubW = 16, kSubH = 8;
+constexpr int kSubCols = kBinW / kSubW, kSubRows = kBinH / kSubH;  // 4 x 8 = 32 sub-tiles
+static_assert(kSubCols * kSubRows == 32, "one sub-tile per warp of a 1024-thread CTA");
 constexpr int VKGSB_BLEND_FP32_MODE = 0, VKGSB_BLEND_UNORM8_MODE = 1;  // == enum vkgsb_blend_mode (include/vkgsb.h)
 
 // ---- resident scene (HBM layout) ---------------------------------------------------------------
@@ -38,9 +43,9 @@ struct FrameParams {
   float cam_model[3];   // inverse(model)*eye / w, projection.comp:85-86 hoisted
   float inv_w, inv_h;   // unused by pinned math (kept for tools)
   uint32_t width, height;
-  uint32_t tiles_x, tiles_y;
+  uint32_t bins_x, bins_y;    // bin grid of the whole image
   uint32_t band_y0, band_y1;  // rows [y0,y1) this renderer bins and blends
-  uint32_t tile_y0, tile_y1;  // tile rows covering the band
+  uint32_t bin_y0, bin_y1;    // bin rows covering the band
 };
 
 // ---- control block: everything the host zeroes with one memset per frame --------------------------------------

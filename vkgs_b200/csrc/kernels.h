@@ -47,17 +47,18 @@ uint32_t sort_max_parts(uint32_t max_n);
 size_t sort_lookback_bytes(uint32_t max_n, int npass);
 void launch_sort(const SortArgs& a, cudaStream_t stream);
 
-// ---- bin.cu: (tile, splat) pairs in front-to-back order + per-tile ranges ------------------------------------------
+// ---- bin.cu: raster records + (bin, rank) pairs in front-to-back order + per-bin ranges ---------------------------
 uint32_t pairs_num_blocks(uint32_t max_visible);
 void launch_make_pairs(const FrameParams* d_fp, Control* d_ctrl, unsigned long long* d_scan_desc,
                        const uint32_t* d_sorted_slots, const float* d_inst, uint32_t max_visible, uint64_t max_pairs,
-                       uint32_t* d_pair_tile, uint32_t* d_pair_slot, cudaStream_t stream);
-void launch_tile_ranges(const Control* d_ctrl, const uint32_t* d_pair_tile_sorted, uint64_t max_pairs,
-                        uint2* d_ranges, cudaStream_t stream);
+                       float* d_rrec, uint32_t* d_pair_bin, uint32_t* d_pair_rank, cudaStream_t stream);
+void launch_bin_ranges(const Control* d_ctrl, const uint32_t* d_pair_bin_sorted, uint64_t max_pairs, uint2* d_ranges,
+                       cudaStream_t stream);
 
 // ---- blend.cu ------------------------------------------------------------------------------------------------------
-void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_slot,
-                  const float* d_inst, int blend_mode, int bgra, uint8_t* d_image, cudaStream_t stream);
+void blend_configure();  // once per device: opt in to > 48 KB dynamic shared memory
+void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_rank,
+                  const float* d_rrec, int blend_mode, int bgra, uint8_t* d_image, cudaStream_t stream);
 
 // ---- misc ----------------------------------------------------------------------------------------------------------
 void launch_gather_sorted(const Control* d_ctrl, const uint32_t* d_sorted_slots, const uint32_t* d_vis_id,

@@ -59,7 +59,8 @@ struct vkgsb_renderer {
   // per-frame work buffers
   uint32_t *keys = nullptr, *slots = nullptr, *keys_alt = nullptr, *slots_alt = nullptr, *vis_id = nullptr;
   float* inst = nullptr;
-  uint32_t *pair_tile = nullptr, *pair_slot = nullptr, *pair_tile_alt = nullptr, *pair_slot_alt = nullptr;
+  float* rrec = nullptr;  // raster records by front-to-back rank (bin.cu)
+  uint32_t *pair_bin = nullptr, *pair_rank = nullptr, *pair_bin_alt = nullptr, *pair_rank_alt = nullptr;
   uint32_t *lookback_depth = nullptr, *lookback_tile = nullptr;
   uint8_t* zero_region = nullptr;  // Control | scan descriptors (project) | scan descriptors (pairs) | tile ranges
   size_t zero_bytes = 0;
@@ -241,14 +242,14 @@ void fill_params(vkgsb_renderer* r) {
   p.height = r->height;
   p.inv_w = 1.f / static_cast<float>(r->width);
   p.inv_h = 1.f / static_cast<float>(r->height);
-  p.tiles_x = (r->width + kTile - 1) / kTile;
-  p.tiles_y = (r->height + kTile - 1) / kTile;
+  p.bins_x = (r->width + kBinW - 1) / kBinW;
+  p.bins_y = (r->height + kBinH - 1) / kBinH;
   p.band_y0 = std::min(r->band_y0, r->height);
   p.band_y1 = (r->band_y1 == 0 || r->band_y1 > r->height) ? r->height : r->band_y1;
   if (p.band_y1 < p.band_y0) p.band_y1 = p.band_y0;
-  p.tile_y0 = p.band_y0 / kTile;
-  p.tile_y1 = (p.band_y1 + kTile - 1) / kTile;
-  if (p.band_y1 == p.band_y0) p.tile_y1 = p.tile_y0;
+  p.bin_y0 = p.band_y0 / kBinH;
+  p.bin_y1 = (p.band_y1 + kBinH - 1) / kBinH;
+  if (p.band_y1 == p.band_y0) p.bin_y1 = p.bin_y0;
 }
 
 // Stage kernels of one frame on `s`.  With `timed`, CUDA events bracket the stages (ev[0..4]).
@@ -267,17 +268,23 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   depth.begin_bit = 0; depth.npass = 4;
   launch_sort(depth, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[2], s));
-  launch_make_pairs(r->d_fp, r->ctrl, r->desc_pairs, r->slots, r->inst, n, r->max_pairs, r->pair_tile, r->pair_slot, s);
-  SortArgs tiles{};
-  tiles.d_count = &r->ctrl->pair_count;
-  tiles.max_n = static_cast<uint32_t>(r->max_pairs);
-  tiles.keys = r->pair_tile; tiles.vals = r->pair_slot; tiles.keys_alt = r->pair_tile_alt; tiles.vals_alt = r->pair_slot_alt;
-  tiles.hist = r->ctrl->hist_tile; tiles.tickets = r->ctrl->sort_ticket + 4; tiles.lookback = r->lookback_tile;
-  tiles.begin_bit = 0; tiles.npass = 2;  // tile ids < 2^16 (<= 240 x 135 tiles at 3840 x 2160)
-  launch_sort(tiles, s);
-  launch_tile_ranges(r->ctrl, r->pair_tile, r->max_pairs, r->ranges, s);
+  launch_make_pairs(r->d_fp, r->ctrl, r->desc_pairs, r->slots, r->inst, n, r->max_pairs, r->rrec, r->pair_bin,
+                    r->pair_rank, s);
+  const uint32_t nbins = r->h_fp.bins_x * (r->h_fp.bin_y1 - r->h_fp.bin_y0);
+  SortArgs bins{};
+  bins.d_count = &r->ctrl->pair_count;
+  bins.max_n = static_cast<uint32_t>(r->max_pairs);
+  bins.keys = r->pair_bin; bins.vals = r->pair_rank; bins.keys_alt = r->pair_bin_alt; bins.vals_alt = r->pair_rank_alt;
+  bins.hist = r->ctrl->hist_tile; bins.tickets = r->ctrl->sort_ticket + 4; bins.lookback = r->lookback_tile;
+  bins.begin_bit = 0;
+  bins.npass = nbins <= 256 ? 1 : 2;  // bin ids < 2^16 (60 x 34 bins at 3840 x 2160)
+  launch_sort(bins, s);
+  // an odd pass count leaves the sorted pairs in the ping-pong buffers
+  const uint32_t* sorted_bin = (bins.npass & 1) ? r->pair_bin_alt : r->pair_bin;
+  const uint32_t* sorted_rank = (bins.npass & 1) ? r->pair_rank_alt : r->pair_rank;
+  launch_bin_ranges(r->ctrl, sorted_bin, r->max_pairs, r->ranges, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[3], s));
-  launch_blend(r->d_fp, r->h_fp, r->ranges, r->pair_slot, r->inst, r->blend_mode,
+  launch_blend(r->d_fp, r->h_fp, r->ranges, sorted_rank, r->rrec, r->blend_mode,
                r->pixel_format == VKGSB_FORMAT_BGRA8, r->image, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[4], s));
   CU_TRY(cudaMemcpyAsync(r->h_counts, r->ctrl, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -356,7 +363,7 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   r->max_splats = cfg->max_splats ? cfg->max_splats : (1u << 23);
   r->max_width = cfg->max_width ? cfg->max_width : 3840;
   r->max_height = cfg->max_height ? cfg->max_height : 2160;
-  r->max_pairs = cfg->max_pairs ? cfg->max_pairs : 16ull * r->max_splats;
+  r->max_pairs = cfg->max_pairs ? cfg->max_pairs : 8ull * r->max_splats;
   if (r->max_pairs > (1ull << 31)) r->max_pairs = 1ull << 31;
   if (r->max_pairs < 4096) r->max_pairs = 4096;
 
@@ -380,10 +387,11 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   ALLOC(r->keys, N * 4); ALLOC(r->slots, N * 4); ALLOC(r->keys_alt, N * 4); ALLOC(r->slots_alt, N * 4);
   ALLOC(r->vis_id, N * 4);
   ALLOC(r->inst, N * 48);
-  ALLOC(r->pair_tile, P * 4); ALLOC(r->pair_slot, P * 4); ALLOC(r->pair_tile_alt, P * 4); ALLOC(r->pair_slot_alt, P * 4);
+  ALLOC(r->rrec, N * 48);
+  ALLOC(r->pair_bin, P * 4); ALLOC(r->pair_rank, P * 4); ALLOC(r->pair_bin_alt, P * 4); ALLOC(r->pair_rank_alt, P * 4);
   ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats, 4));
   ALLOC(r->lookback_tile, sort_lookback_bytes(static_cast<uint32_t>(P), 2));
-  const size_t max_tiles = static_cast<size_t>((r->max_width + kTile - 1) / kTile) * ((r->max_height + kTile - 1) / kTile);
+  const size_t max_tiles = static_cast<size_t>((r->max_width + kBinW - 1) / kBinW) * ((r->max_height + kBinH - 1) / kBinH);
   const size_t nb_proj = project_num_blocks(r->max_splats), nb_pairs = pairs_num_blocks(r->max_splats);
   const size_t ctrl_bytes = (sizeof(Control) + 255) & ~size_t(255);
   r->zero_bytes = ctrl_bytes + (nb_proj + nb_pairs) * 8 + max_tiles * sizeof(uint2);
@@ -402,6 +410,7 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   for (auto& ev : r->chunk_done)
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  blend_configure();
   r->loader = std::thread(loader_main, r);
   *out = r;
   return VKGSB_OK;
@@ -423,7 +432,7 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   if (r->load_stream) cudaStreamSynchronize(r->load_stream);
   if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
   void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
-                 r->vis_id, r->inst, r->pair_tile, r->pair_slot, r->pair_tile_alt, r->pair_slot_alt, r->lookback_depth,
+                 r->vis_id, r->inst, r->rrec, r->pair_bin, r->pair_rank, r->pair_bin_alt, r->pair_rank_alt, r->lookback_depth,
                  r->lookback_tile, r->zero_region, r->d_fp, r->image, r->d_offsets, r->d_rows[0], r->d_rows[1]};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -527,7 +536,7 @@ int vkgsb_set_viewport(vkgsb_renderer* r, uint32_t width, uint32_t height) {
   if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
   if (width == 0 || height == 0) return fail(VKGSB_ERR_INVALID, "empty viewport");
   if (static_cast<size_t>(width) * height > static_cast<size_t>(r->max_width) * r->max_height ||
-      (width + kTile - 1) / kTile > 1023 || (height + kTile - 1) / kTile > 1023)
+      (width + kBinW - 1) / kBinW > 255 || (height + kBinH - 1) / kBinH > 255)
     return fail(VKGSB_ERR_CAPACITY, "viewport larger than the renderer was created for");
   if (width != r->width || height != r->height) {
     std::lock_guard<std::mutex> g(r->draw_mutex);
