@@ -95,7 +95,9 @@ enum vkgsb_option {
   VKGSB_OPT_BLEND_MODE = 1,   /* vkgsb_blend_mode */
   VKGSB_OPT_PIXEL_FORMAT = 2, /* vkgsb_pixel_format */
   VKGSB_OPT_BAND_Y0 = 3,      /* restrict binning + blending to image rows [y0,y1) (tile-band sharding) */
-  VKGSB_OPT_BAND_Y1 = 4       /* 0 => full height */
+  VKGSB_OPT_BAND_Y1 = 4,      /* 0 => full height */
+  VKGSB_OPT_KEEP_INSTANCES = 5 /* 1: also store the reference-format instance records (projection.comp:177-179) so
+                                  vkgsb_read_instances can return them; off by default (48 B/visible splat of writes) */
 };
 
 VKGSB_API const char* vkgsb_last_error(void);

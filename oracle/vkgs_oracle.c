@@ -23,10 +23,13 @@
  *
  * All paths cited below are relative to /root/reference.
  *
- * ARITHMETIC PIN.  IEEE binary32 throughout, one rounding per written operator,
- * no FMA contraction (compile with -ffp-contract=off), operands evaluated in the
- * order GLSL writes them (mat*vec = sum over columns, left to right).  The CUDA
- * kernels use __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn in the same order, so
+ * ARITHMETIC PIN.  IEEE binary32 throughout, operands evaluated in the order GLSL
+ * writes them (mat*vec = sum over columns, left to right).  A sum of products is
+ * ONE explicit fused chain, s = a0*b0; s = fma(a1,b1,s); s = fma(a2,b2,s) ... -
+ * what a GPU shader compiler emits for GLSL's mat*vec / mat*mat / dot - and
+ * nothing else is ever contracted (compile with -ffp-contract=off; fmaf() is the
+ * only source of FMAs).  The CUDA kernels spell the same chains with fmaf() in a
+ * translation unit built with -fmad=false, and IEEE division / square root, so
  * visible count, keys, ids and instance records are bit-exact against this
  * file.  Transcendentals (exp in activation and in the fragment alpha) are not
  * correctly rounded on any device and are tolerance-checked.
@@ -50,12 +53,12 @@ static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float h2f(uint16_t h) { _Float16 x; memcpy(&x, &h, 2); return (float)x; }
 static inline uint16_t f2h(float f) { _Float16 x = (_Float16)f; uint16_t h; memcpy(&h, &x, 2); return h; }
 
-/* C = A*B for column-major 3x3 stored as m[c*3+r]; element = ((a0*b0 + a1*b1) + a2*b2). */
+/* C = A*B for column-major 3x3 stored as m[c*3+r]; element = fma(a2,b2, fma(a1,b1, a0*b0)). */
 static void mat3_mul(const float* A, const float* B, float* C) {
   float t[9];
   for (int c = 0; c < 3; ++c)
     for (int r = 0; r < 3; ++r)
-      t[c * 3 + r] = (A[0 * 3 + r] * B[c * 3 + 0] + A[1 * 3 + r] * B[c * 3 + 1]) + A[2 * 3 + r] * B[c * 3 + 2];
+      t[c * 3 + r] = fmaf(A[2 * 3 + r], B[c * 3 + 2], fmaf(A[1 * 3 + r], B[c * 3 + 1], A[0 * 3 + r] * B[c * 3 + 0]));
   memcpy(C, t, sizeof t);
 }
 static void mat3_transpose(const float* A, float* T) {
@@ -69,15 +72,15 @@ static void mat4_mul(const float* A, const float* B, float* C) {
   float t[16];
   for (int c = 0; c < 4; ++c)
     for (int r = 0; r < 4; ++r)
-      t[c * 4 + r] = ((A[0 * 4 + r] * B[c * 4 + 0] + A[1 * 4 + r] * B[c * 4 + 1]) + A[2 * 4 + r] * B[c * 4 + 2]) +
-                     A[3 * 4 + r] * B[c * 4 + 3];
+      t[c * 4 + r] = fmaf(A[3 * 4 + r], B[c * 4 + 3],
+                          fmaf(A[2 * 4 + r], B[c * 4 + 2], fmaf(A[1 * 4 + r], B[c * 4 + 1], A[0 * 4 + r] * B[c * 4 + 0])));
   memcpy(C, t, sizeof t);
 }
 /* r = M*v */
 static void mat4_vec(const float* M, const float* v, float* r) {
   float t[4];
   for (int i = 0; i < 4; ++i)
-    t[i] = ((M[0 * 4 + i] * v[0] + M[1 * 4 + i] * v[1]) + M[2 * 4 + i] * v[2]) + M[3 * 4 + i] * v[3];
+    t[i] = fmaf(M[3 * 4 + i], v[3], fmaf(M[2 * 4 + i], v[2], fmaf(M[1 * 4 + i], v[1], M[0 * 4 + i] * v[0])));
   memcpy(r, t, sizeof t);
 }
 static void mat3_of_mat4(const float* M, float* m3) {
@@ -259,7 +262,7 @@ static void project_one(const vko_camera* cam, const float* cam_m, const float* 
                         float opac, const uint16_t* sh48, int variant, float* inst) {
   /* dir = normalize(pos - cam_model)   projection.comp:87 */
   float dx = pos3[0] - cam_m[0], dy = pos3[1] - cam_m[1], dz = pos3[2] - cam_m[2];
-  float dl = sqrtf((dx * dx + dy * dy) + dz * dz);
+  float dl = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
   float x = dx / dl, y = dy / dl, z = dz / dl;
 
   /* cov3d = mat3(v0, v0.y, v1.xy, v0.z, v1.yz)   projection.comp:92 */
@@ -278,19 +281,27 @@ static void project_one(const vko_camera* cam, const float* cam_m, const float* 
 
   /* projection.comp:105-109 */
   float px = pv[0], py = pv[1], pz = pv[2];
-  float r = sqrtf((px * px + py * py) + pz * pz);
+  float r = sqrtf(fmaf(pz, pz, fmaf(py, py, px * px)));
   float J[9] = {-1.f / pz, 0.f, -2.f * px / r, 0.f, -1.f / pz, -2.f * py / r, px / pz / pz, py / pz / pz, -2.f * pz / r};
-  mat3_mul(J, c3, c3);
-  mat3_transpose(J, t3);
-  mat3_mul(c3, t3, c3);
+  /* cov3d = J * cov3d * transpose(J); only its upper-left 2x2 is read afterwards (mat2(cov3d), :112), so only the
+   * elements that feed it are evaluated - each by the same chain the full product would use. */
+  {
+    float T[9]; /* T = J * cov3d, rows 0 and 1 */
+    for (int cc = 0; cc < 3; ++cc)
+      for (int rr = 0; rr < 2; ++rr)
+        T[cc * 3 + rr] = fmaf(J[2 * 3 + rr], c3[cc * 3 + 2], fmaf(J[1 * 3 + rr], c3[cc * 3 + 1], J[0 * 3 + rr] * c3[cc * 3 + 0]));
+    for (int cc = 0; cc < 2; ++cc)   /* (T * J^T)[cc][rr] = sum_k T[k][rr] * J[k][cc] */
+      for (int rr = 0; rr < 2; ++rr)
+        c3[cc * 3 + rr] = fmaf(T[2 * 3 + rr], J[2 * 3 + cc], fmaf(T[1 * 3 + rr], J[1 * 3 + cc], T[0 * 3 + rr] * J[0 * 3 + cc]));
+  }
 
   /* cov2d = mat2(proj) * mat2(cov3d) * mat2(proj)   :112-113; 2x2 column-major m[c*2+r] */
   float ps[4] = {cam->proj[0], cam->proj[1], cam->proj[4], cam->proj[5]};
   float c2[4] = {c3[0], c3[1], c3[3], c3[4]}, t2[4], cov2d[4];
   for (int c = 0; c < 2; ++c)
-    for (int rr = 0; rr < 2; ++rr) t2[c * 2 + rr] = ps[0 * 2 + rr] * c2[c * 2 + 0] + ps[1 * 2 + rr] * c2[c * 2 + 1];
+    for (int rr = 0; rr < 2; ++rr) t2[c * 2 + rr] = fmaf(ps[1 * 2 + rr], c2[c * 2 + 1], ps[0 * 2 + rr] * c2[c * 2 + 0]);
   for (int c = 0; c < 2; ++c)
-    for (int rr = 0; rr < 2; ++rr) cov2d[c * 2 + rr] = t2[0 * 2 + rr] * ps[c * 2 + 0] + t2[1 * 2 + rr] * ps[c * 2 + 1];
+    for (int rr = 0; rr < 2; ++rr) cov2d[c * 2 + rr] = fmaf(t2[1 * 2 + rr], ps[c * 2 + 1], t2[0 * 2 + rr] * ps[c * 2 + 0]);
   /* low-pass   :116-117 */
   float fw = (float)cam->width, fh = (float)cam->height;
   cov2d[0] = cov2d[0] + 1.f / fw / fw;
@@ -298,7 +309,7 @@ static void project_one(const vko_camera* cam, const float* cam_m, const float* 
 
   /* eigendecomposition   :122-134 */
   float a = cov2d[0], b = cov2d[3], c = cov2d[2];
-  float D = sqrtf((a - b) * (a - b) + 4.f * c * c);
+  float D = sqrtf(fmaf(4.f * c, c, (a - b) * (a - b)));
   float s0 = sqrtf(0.5f * ((a + b) + D));
   float s1 = sqrtf(0.5f * ((a + b) - D));
   float sin2t = 2.f * c / D, cos2t = (a - b) / D;
@@ -342,8 +353,8 @@ static void project_one(const vko_camera* cam, const float* cam_m, const float* 
     const uint16_t* s = sh48 + 16 * ch;
     float q[4];
     for (int g = 0; g < 4; ++g)
-      q[g] = ((bs[4 * g + 0] * h2f(s[4 * g + 0]) + bs[4 * g + 1] * h2f(s[4 * g + 1])) +
-              bs[4 * g + 2] * h2f(s[4 * g + 2])) + bs[4 * g + 3] * h2f(s[4 * g + 3]);
+      q[g] = fmaf(bs[4 * g + 3], h2f(s[4 * g + 3]),
+                  fmaf(bs[4 * g + 2], h2f(s[4 * g + 2]), fmaf(bs[4 * g + 1], h2f(s[4 * g + 1]), bs[4 * g + 0] * h2f(s[4 * g + 0]))));
     float cc = ((q[0] + q[1]) + q[2]) + q[3];
     cc = cc + 0.5f;
     col[ch] = cc > 0.f ? cc : 0.f; /* max(color + 0.5, 0); NaN -> 0 like GLSL max(NaN,0) is undefined, pin 0 */

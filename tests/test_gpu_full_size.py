@@ -16,6 +16,7 @@ def c2():
     rows = synth.scene_bicycle()
     r = vkgs_b200.Renderer(max_splats=rows.shape[0], max_width=1600, max_height=900)
     r.upload_splats(rows)
+    r.set_option(vkgs_b200.OPT_KEEP_INSTANCES, 1)
     del rows
     yield r
     r.close()

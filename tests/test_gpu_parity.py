@@ -33,6 +33,7 @@ def bits(a):
 @pytest.fixture(scope="module")
 def small_renderer():
     r = vkgs_b200.Renderer(max_splats=1 << 17, max_width=1024, max_height=768, max_pairs=1 << 24)
+    r.set_option(vkgs_b200.OPT_KEEP_INSTANCES, 1)      # parity tap: reference-format instance records
     yield r
     r.close()
 
@@ -326,3 +327,19 @@ def test_malformed_ply_is_rejected(tmp_path, small_renderer):
     with pytest.raises(vkgs_b200.VkgsbError) as e:
         small_renderer.load_ply(str(good))
     assert e.value.code == 3
+
+
+def test_instances_tap_needs_the_option(c1):
+    rows, P, V, E = c1
+    with vkgs_b200.Renderer(max_splats=4096, max_width=128, max_height=128, max_pairs=1 << 18) as r:
+        r.upload_splats(rows[:4000])
+        r.set_viewport(128, 96)
+        r.set_camera(P, V, E)
+        r.draw()
+        with pytest.raises(vkgs_b200.VkgsbError):
+            r.read_instances()                                           # not kept by default
+        r.set_option(vkgs_b200.OPT_KEEP_INSTANCES, 1)
+        a = r.draw().copy()
+        assert r.read_instances().shape[1] == 12
+        r.set_option(vkgs_b200.OPT_KEEP_INSTANCES, 0)
+        assert np.array_equal(r.draw(), a)                               # the tap does not change the image

@@ -11,7 +11,9 @@ constexpr int kTile = 16;              // origin granularity of the pinned fragm
 // Binning granularity: one CTA of the blend stage owns a kBinW x kBinH pixel bin and splits it into 32 sub-tiles of
 // kSubW x kSubH pixels, one per warp (4 pixels per lane).
 constexpr int kBinW = 64, kBinH = 64, kSubW = 16, kSubH = 8;
+constexpr uint32_t kFlagKeepInstances = 1u;  // also write the reference-format instance records (parity tap)
 constexpr int kSubCols = kBinW / kSubW, kSubRows = kBinH / kSubH;  // 4 x 8 = 32 sub-tiles
+constexpr int kMaxBins = 4096;  // 64 x 64 bins of 64 x 64 px: up to 4096 x 4096 images
 static_assert(kSubCols * kSubRows == 32, "one sub-tile per warp of a 1024-thread CTA");
 constexpr int VKGSB_BLEND_FP32_MODE = 0, VKGSB_BLEND_UNORM8_MODE = 1;  // == enum vkgsb_blend_mode (include/vkgsb.h)
 
@@ -41,7 +43,8 @@ struct FrameParams {
   float model[16];
   float pvm[16];        // (proj*view)*model composed on the host, rank.comp:32
   float cam_model[3];   // inverse(model)*eye / w, projection.comp:85-86 hoisted
-  float inv_w, inv_h;   // unused by pinned math (kept for tools)
+  uint32_t flags;       // kFlagKeepInstances
+  uint32_t pad0;
   uint32_t width, height;
   uint32_t bins_x, bins_y;    // bin grid of the whole image
   uint32_t band_y0, band_y1;  // rows [y0,y1) this renderer bins and blends
@@ -58,7 +61,8 @@ struct Control {
   uint32_t sort_ticket[8];  // [0..3] depth passes, [4..7] tile passes
   uint32_t pad[3];
   uint32_t hist_depth[4 * 256];
-  uint32_t hist_tile[4 * 256];
+  uint32_t hist_bin[4 * 256];
+  uint32_t bin_count[kMaxBins];  // (bin, splat) pairs per bin, accumulated by k_make_pairs
 };
 
 // ---- decoupled look-back descriptor for the two ordered block scans (visible slots, pair offsets) --------------

@@ -1,8 +1,10 @@
-// Host-side matrix helpers for the per-frame parameter block.  Column-major float[16] (m[c*4+r]), one binary32
-// rounding per operator, sums associated left to right - the order rank.comp:32 / projection.comp:85 write and
-// oracle/vkgs_oracle.c pins.  Build with -ffp-contract=off.
+// Host-side matrix helpers for the per-frame parameter block.  Column-major float[16] (m[c*4+r]); a sum of products
+// is one explicit fused chain (a0*b0, then fma per further term, left to right) in the order rank.comp:32 /
+// projection.comp:85 write, exactly as oracle/vkgs_oracle.c pins it.  Build with -ffp-contract=off: std::fmaf is
+// the only source of FMAs.
 #pragma once
 
+#include <cmath>
 #include <cstring>
 
 namespace vkgsb {
@@ -11,15 +13,16 @@ inline void mat4_mul(const float* A, const float* B, float* C) {
   float t[16];
   for (int c = 0; c < 4; ++c)
     for (int r = 0; r < 4; ++r)
-      t[c * 4 + r] = ((A[0 * 4 + r] * B[c * 4 + 0] + A[1 * 4 + r] * B[c * 4 + 1]) + A[2 * 4 + r] * B[c * 4 + 2]) +
-                     A[3 * 4 + r] * B[c * 4 + 3];
+      t[c * 4 + r] = std::fmaf(A[3 * 4 + r], B[c * 4 + 3],
+                               std::fmaf(A[2 * 4 + r], B[c * 4 + 2],
+                                         std::fmaf(A[1 * 4 + r], B[c * 4 + 1], A[0 * 4 + r] * B[c * 4 + 0])));
   std::memcpy(C, t, sizeof t);
 }
 
 inline void mat4_vec(const float* M, const float* v, float* out) {
   float t[4];
   for (int i = 0; i < 4; ++i)
-    t[i] = ((M[0 * 4 + i] * v[0] + M[1 * 4 + i] * v[1]) + M[2 * 4 + i] * v[2]) + M[3 * 4 + i] * v[3];
+    t[i] = std::fmaf(M[3 * 4 + i], v[3], std::fmaf(M[2 * 4 + i], v[2], std::fmaf(M[1 * 4 + i], v[1], M[0 * 4 + i] * v[0])));
   std::memcpy(out, t, sizeof t);
 }
 

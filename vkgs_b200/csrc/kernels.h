@@ -26,8 +26,11 @@ void launch_export_scene(const SceneStorage& src, uint32_t n, float* d_pos, floa
 
 // ---- project.cu ------------------------------------------------------------------------------------------------
 uint32_t project_num_blocks(uint32_t n);
+// d_rrec: 3 x float4 raster record per visible slot; d_inst: 12-float instance record (written only when
+// FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control.
 void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl, unsigned long long* d_scan_desc,
-                    uint32_t* d_keys, uint32_t* d_slots, uint32_t* d_vis_id, float* d_inst, cudaStream_t stream);
+                    uint32_t* d_keys, uint32_t* d_slots, uint32_t* d_vis_id, float* d_rrec, float* d_inst,
+                    cudaStream_t stream);
 
 // ---- sort.cu: onesweep LSD radix sort, count read on the device ----------------------------------------------------
 struct SortArgs {
@@ -37,9 +40,11 @@ struct SortArgs {
   uint32_t* vals;
   uint32_t* keys_alt;       // ping-pong scratch, max_n each
   uint32_t* vals_alt;
-  uint32_t* hist;           // [npass][256], zero on entry
+  uint32_t* hist;           // [npass][256]; zero on entry, or already filled when have_hist
   uint32_t* tickets;        // [npass], zero on entry
-  uint32_t* lookback;       // [npass][sort_max_parts(max_n)][256]; cleared by the histogram kernel
+  uint32_t* lookback;       // [npass][sort_max_parts(max_n)][256]; cleared by the histogram kernel, or by the
+                            // caller when have_hist
+  bool have_hist;           // the producer of the keys already built the digit histograms: no histogram pass
   int begin_bit;            // first pass digit starts here; passes are 8 bits wide
   int npass;                // 2 or 4
 };
@@ -47,17 +52,17 @@ uint32_t sort_max_parts(uint32_t max_n);
 size_t sort_lookback_bytes(uint32_t max_n, int npass);
 void launch_sort(const SortArgs& a, cudaStream_t stream);
 
-// ---- bin.cu: raster records + (bin, rank) pairs in front-to-back order + per-bin ranges ---------------------------
+// ---- bin.cu: (bin, slot) pairs in front-to-back order, per-bin ranges and digit histograms ------------------------
 uint32_t pairs_num_blocks(uint32_t max_visible);
 void launch_make_pairs(const FrameParams* d_fp, Control* d_ctrl, unsigned long long* d_scan_desc,
-                       const uint32_t* d_sorted_slots, const float* d_inst, uint32_t max_visible, uint64_t max_pairs,
-                       float* d_rrec, uint32_t* d_pair_bin, uint32_t* d_pair_rank, cudaStream_t stream);
-void launch_bin_ranges(const Control* d_ctrl, const uint32_t* d_pair_bin_sorted, uint64_t max_pairs, uint2* d_ranges,
-                       cudaStream_t stream);
+                       const uint32_t* d_sorted_slots, const float* d_rrec, uint32_t max_visible, uint64_t max_pairs,
+                       uint32_t* d_pair_bin, uint32_t* d_pair_slot, cudaStream_t stream);
+void launch_bin_scan(const FrameParams* d_fp, Control* d_ctrl, uint2* d_ranges, uint32_t* d_lookback, uint64_t max_pairs,
+                     int npass, cudaStream_t stream);
 
 // ---- blend.cu ------------------------------------------------------------------------------------------------------
 void blend_configure();  // once per device: opt in to > 48 KB dynamic shared memory
-void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_rank,
+void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_slot,
                   const float* d_rrec, int blend_mode, int bgra, uint8_t* d_image, cudaStream_t stream);
 
 // ---- misc ----------------------------------------------------------------------------------------------------------

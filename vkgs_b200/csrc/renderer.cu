@@ -60,8 +60,8 @@ struct vkgsb_renderer {
   uint32_t *keys = nullptr, *slots = nullptr, *keys_alt = nullptr, *slots_alt = nullptr, *vis_id = nullptr;
   float* inst = nullptr;
   float* rrec = nullptr;  // raster records by front-to-back rank (bin.cu)
-  uint32_t *pair_bin = nullptr, *pair_rank = nullptr, *pair_bin_alt = nullptr, *pair_rank_alt = nullptr;
-  uint32_t *lookback_depth = nullptr, *lookback_tile = nullptr;
+  uint32_t *pair_bin = nullptr, *pair_slot = nullptr, *pair_bin_alt = nullptr, *pair_slot_alt = nullptr;
+  uint32_t *lookback_depth = nullptr, *lookback_bin = nullptr;
   uint8_t* zero_region = nullptr;  // Control | scan descriptors (project) | scan descriptors (pairs) | tile ranges
   size_t zero_bytes = 0;
   Control* ctrl = nullptr;
@@ -82,7 +82,8 @@ struct vkgsb_renderer {
   vkgsb_camera cam{};
   bool have_cam = false;
   uint32_t width = 0, height = 0;
-  int blend_mode = VKGSB_BLEND_FP32, pixel_format = VKGSB_FORMAT_RGBA8, stage_timing = 0;
+  int blend_mode = VKGSB_BLEND_FP32, pixel_format = VKGSB_FORMAT_RGBA8, stage_timing = 0, keep_instances = 0;
+  bool last_frame_has_instances = false;
   uint32_t band_y0 = 0, band_y1 = 0;
   FrameParams h_fp{};
   cudaGraphExec_t graph_exec = nullptr;
@@ -240,8 +241,8 @@ void fill_params(vkgsb_renderer* r) {
   p.cam_model[2] = cm[2] / cm[3];
   p.width = r->width;
   p.height = r->height;
-  p.inv_w = 1.f / static_cast<float>(r->width);
-  p.inv_h = 1.f / static_cast<float>(r->height);
+  p.flags = r->keep_instances ? kFlagKeepInstances : 0u;
+  p.pad0 = 0u;
   p.bins_x = (r->width + kBinW - 1) / kBinW;
   p.bins_y = (r->height + kBinH - 1) / kBinH;
   p.band_y0 = std::min(r->band_y0, r->height);
@@ -257,8 +258,10 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   const uint32_t n = r->scene_n.load();
   Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.payload, n};
   CU_TRY(cudaMemsetAsync(r->zero_region, 0, r->zero_bytes, s));
+  // look-back words of the depth sort: only partitions of the <= n visible splats can be touched
+  CU_TRY(cudaMemsetAsync(r->lookback_depth, 0, sort_lookback_bytes(n, 4), s));
   if (timed) CU_TRY(cudaEventRecord(r->ev[0], s));
-  launch_project(sc, r->d_fp, r->ctrl, r->desc_project, r->keys, r->slots, r->vis_id, r->inst, s);
+  launch_project(sc, r->d_fp, r->ctrl, r->desc_project, r->keys, r->slots, r->vis_id, r->rrec, r->inst, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
   SortArgs depth{};
   depth.d_count = &r->ctrl->visible_count;
@@ -266,25 +269,25 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   depth.keys = r->keys; depth.vals = r->slots; depth.keys_alt = r->keys_alt; depth.vals_alt = r->slots_alt;
   depth.hist = r->ctrl->hist_depth; depth.tickets = r->ctrl->sort_ticket; depth.lookback = r->lookback_depth;
   depth.begin_bit = 0; depth.npass = 4;
+  depth.have_hist = true;  // k_project accumulated the four digit histograms
   launch_sort(depth, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[2], s));
-  launch_make_pairs(r->d_fp, r->ctrl, r->desc_pairs, r->slots, r->inst, n, r->max_pairs, r->rrec, r->pair_bin,
-                    r->pair_rank, s);
+  launch_make_pairs(r->d_fp, r->ctrl, r->desc_pairs, r->slots, r->rrec, n, r->max_pairs, r->pair_bin, r->pair_slot, s);
   const uint32_t nbins = r->h_fp.bins_x * (r->h_fp.bin_y1 - r->h_fp.bin_y0);
   SortArgs bins{};
   bins.d_count = &r->ctrl->pair_count;
   bins.max_n = static_cast<uint32_t>(r->max_pairs);
-  bins.keys = r->pair_bin; bins.vals = r->pair_rank; bins.keys_alt = r->pair_bin_alt; bins.vals_alt = r->pair_rank_alt;
-  bins.hist = r->ctrl->hist_tile; bins.tickets = r->ctrl->sort_ticket + 4; bins.lookback = r->lookback_tile;
+  bins.keys = r->pair_bin; bins.vals = r->pair_slot; bins.keys_alt = r->pair_bin_alt; bins.vals_alt = r->pair_slot_alt;
+  bins.hist = r->ctrl->hist_bin; bins.tickets = r->ctrl->sort_ticket + 4; bins.lookback = r->lookback_bin;
   bins.begin_bit = 0;
-  bins.npass = nbins <= 256 ? 1 : 2;  // bin ids < 2^16 (60 x 34 bins at 3840 x 2160)
+  bins.npass = nbins <= 256 ? 1 : 2;  // bin ids < 4096
+  bins.have_hist = true;              // k_bin_scan derives them from the per-bin counts
+  launch_bin_scan(r->d_fp, r->ctrl, r->ranges, r->lookback_bin, r->max_pairs, bins.npass, s);
   launch_sort(bins, s);
   // an odd pass count leaves the sorted pairs in the ping-pong buffers
-  const uint32_t* sorted_bin = (bins.npass & 1) ? r->pair_bin_alt : r->pair_bin;
-  const uint32_t* sorted_rank = (bins.npass & 1) ? r->pair_rank_alt : r->pair_rank;
-  launch_bin_ranges(r->ctrl, sorted_bin, r->max_pairs, r->ranges, s);
+  const uint32_t* sorted_slot = (bins.npass & 1) ? r->pair_slot_alt : r->pair_slot;
   if (timed) CU_TRY(cudaEventRecord(r->ev[3], s));
-  launch_blend(r->d_fp, r->h_fp, r->ranges, sorted_rank, r->rrec, r->blend_mode,
+  launch_blend(r->d_fp, r->h_fp, r->ranges, sorted_slot, r->rrec, r->blend_mode,
                r->pixel_format == VKGSB_FORMAT_BGRA8, r->image, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[4], s));
   CU_TRY(cudaMemcpyAsync(r->h_counts, r->ctrl, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -324,6 +327,7 @@ int run_frame(vkgsb_renderer* r, cudaStream_t s) {
     r->ev_recorded = false;
   }
   r->frame_counter++;
+  r->last_frame_has_instances = r->keep_instances != 0;
   return VKGSB_OK;
 }
 
@@ -388,9 +392,9 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   ALLOC(r->vis_id, N * 4);
   ALLOC(r->inst, N * 48);
   ALLOC(r->rrec, N * 48);
-  ALLOC(r->pair_bin, P * 4); ALLOC(r->pair_rank, P * 4); ALLOC(r->pair_bin_alt, P * 4); ALLOC(r->pair_rank_alt, P * 4);
+  ALLOC(r->pair_bin, P * 4); ALLOC(r->pair_slot, P * 4); ALLOC(r->pair_bin_alt, P * 4); ALLOC(r->pair_slot_alt, P * 4);
   ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats, 4));
-  ALLOC(r->lookback_tile, sort_lookback_bytes(static_cast<uint32_t>(P), 2));
+  ALLOC(r->lookback_bin, sort_lookback_bytes(static_cast<uint32_t>(P), 2));
   const size_t max_tiles = static_cast<size_t>((r->max_width + kBinW - 1) / kBinW) * ((r->max_height + kBinH - 1) / kBinH);
   const size_t nb_proj = project_num_blocks(r->max_splats), nb_pairs = pairs_num_blocks(r->max_splats);
   const size_t ctrl_bytes = (sizeof(Control) + 255) & ~size_t(255);
@@ -432,8 +436,8 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   if (r->load_stream) cudaStreamSynchronize(r->load_stream);
   if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
   void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
-                 r->vis_id, r->inst, r->rrec, r->pair_bin, r->pair_rank, r->pair_bin_alt, r->pair_rank_alt, r->lookback_depth,
-                 r->lookback_tile, r->zero_region, r->d_fp, r->image, r->d_offsets, r->d_rows[0], r->d_rows[1]};
+                 r->vis_id, r->inst, r->rrec, r->pair_bin, r->pair_slot, r->pair_bin_alt, r->pair_slot_alt, r->lookback_depth,
+                 r->lookback_bin, r->zero_region, r->d_fp, r->image, r->d_offsets, r->d_rows[0], r->d_rows[1]};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (r->h_counts) cudaFreeHost(r->h_counts);
@@ -461,6 +465,7 @@ int vkgsb_set_option(vkgsb_renderer* r, int option, int64_t value) {
       if (value != VKGSB_FORMAT_RGBA8 && value != VKGSB_FORMAT_BGRA8) return fail(VKGSB_ERR_INVALID, "bad pixel format");
       r->pixel_format = static_cast<int>(value);
       break;
+    case VKGSB_OPT_KEEP_INSTANCES: r->keep_instances = value != 0; break;
     case VKGSB_OPT_BAND_Y0: r->band_y0 = static_cast<uint32_t>(value); break;
     case VKGSB_OPT_BAND_Y1: r->band_y1 = static_cast<uint32_t>(value); break;
     default: return fail(VKGSB_ERR_INVALID, "unknown option");
@@ -536,7 +541,7 @@ int vkgsb_set_viewport(vkgsb_renderer* r, uint32_t width, uint32_t height) {
   if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
   if (width == 0 || height == 0) return fail(VKGSB_ERR_INVALID, "empty viewport");
   if (static_cast<size_t>(width) * height > static_cast<size_t>(r->max_width) * r->max_height ||
-      (width + kBinW - 1) / kBinW > 255 || (height + kBinH - 1) / kBinH > 255)
+      (width + kBinW - 1) / kBinW > 64 || (height + kBinH - 1) / kBinH > 64)
     return fail(VKGSB_ERR_CAPACITY, "viewport larger than the renderer was created for");
   if (width != r->width || height != r->height) {
     std::lock_guard<std::mutex> g(r->draw_mutex);
@@ -646,6 +651,8 @@ int vkgsb_read_instances(vkgsb_renderer* r, float* inst, uint32_t capacity, uint
   *count = v;
   if (v > capacity) return fail(VKGSB_ERR_CAPACITY, "capacity smaller than the visible count");
   if (v == 0 || !inst) return VKGSB_OK;
+  if (!r->last_frame_has_instances)
+    return fail(VKGSB_ERR_INVALID, "instance records were not kept: set VKGSB_OPT_KEEP_INSTANCES before drawing");
   float* tmp = nullptr;
   CU_TRY(cudaMalloc(&tmp, v * 48ull));
   launch_gather_sorted(r->ctrl, r->slots, r->vis_id, r->inst, v, nullptr, tmp, r->stream);
