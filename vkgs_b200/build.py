@@ -81,7 +81,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    _build_pygs(force)
     return LIB
+
+
+def _build_pygs(force: bool) -> str:
+    """pygs/_pygs_cpp.so: the native half of the `pygs` package (pybind11 over vkgs::Engine), linked against libvkgsb."""
+    import sysconfig
+
+    import pybind11
+    src = os.path.join(ROOT, "pygs", "_pygs_cpp.cc")
+    out = os.path.join(ROOT, "pygs", "_pygs_cpp.so")
+    if not os.path.exists(src):
+        return ""
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return out
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-I", pybind11.get_include(),
+           "-I", sysconfig.get_paths()["include"], "-I", os.path.join(ROOT, "include"), src,
+           "-L", os.path.dirname(LIB), "-lvkgsb", "-Wl,-rpath,$ORIGIN/../vkgs_b200/lib", "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"pygs build failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 if __name__ == "__main__":
