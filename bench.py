@@ -33,7 +33,7 @@ WIDTH, HEIGHT = 1600, 900
 N_SPLATS = 6_131_954
 N_VIEWS = 64                      # orbit the steps cycle through
 ORBIT = dict(r=1.5, phi_deg=70.0)  # ~2 M visible of 6.1 M: the reference's "view 2" regime (DETAILS.md:72)
-KERNELS_PER_FRAME = 11            # set_params, project, 4 depth onesweep passes, make_pairs, bin_scan, 2 bin onesweep passes, blend
+KERNELS_PER_FRAME = 10            # set_params, project, 4 depth onesweep passes, bin count / scan / place, blend
 
 
 def view_camera(i):

@@ -3,8 +3,8 @@
 // SRC_ALPHA / ONE_MINUS_SRC_ALPHA for colour AND alpha (engine.cc:281-289), clear (0,0,0,1) (engine.cc:1382-1387),
 // depth LESS / no write (graphics_pipeline.cc:79-81; applied in bin.cu), B8G8R8A8_UNORM target (render_pass.cc:15).
 //
-// One 1024-thread CTA per 64x64-pixel bin streams the bin's nearest-first splat list in batches of 1024 through
-// shared memory.  While staging, each thread turns its splat's pixel bounding box into a 32-bit mask over the bin's
+// One 1024-thread CTA per 64x64-pixel bin streams the nearest-first splat list of the COARSE bin it lies in (bin.cu)
+// in batches of 1024 through shared memory.  While staging, each thread turns its splat's pixel bounding box into a 32-bit mask over the bin's
 // 4x8 sub-tiles (16x8 pixels, one per warp); each warp then picks its splats out of the batch with one ballot per
 // 32 entries and shades them, 4 pixels per lane.  So a splat only costs the warps it can touch, and a warp whose 128
 // pixels are all saturated drops out of the masks; the CTA stops when every warp has.
@@ -40,6 +40,8 @@ __device__ __forceinline__ uint32_t pack_pixel(uint32_t r, uint32_t g, uint32_t 
 // 32-bit mask (bit = row * 4 + col) of the bin's sub-tiles a pixel box [x0,x1] x [y0,y1] touches.
 __device__ __forceinline__ uint32_t subtile_mask(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, uint32_t bin_x,
                                                  uint32_t bin_y) {
+  // entries come from the coarse bin's list: most boxes miss this 64x64 bin altogether (also the empty box x0 > x1)
+  if (x1 < bin_x || x0 >= bin_x + kBinW || y1 < bin_y || y0 >= bin_y + kBinH || x0 > x1 || y0 > y1) return 0u;
   const int c0 = max(static_cast<int>(x0) - static_cast<int>(bin_x), 0) / kSubW;
   const int c1 = min(static_cast<int>(x1) - static_cast<int>(bin_x), kBinW - 1) / kSubW;
   const int r0 = max(static_cast<int>(y0) - static_cast<int>(bin_y), 0) / kSubH;
@@ -78,7 +80,7 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
     fly[k] = static_cast<float>(y - org_y);
     inside[k] = x < width && y >= band_y0 && y < band_y1;
   }
-  const uint2 range = ranges[bin];
+  const uint2 range = ranges[((bin_y >> fpp->cshift_y) - fpp->cbin_y0) * fpp->cbins_x + (bin_x >> fpp->cshift_x)];
   const uint32_t wbit = 1u << warp;
 
   if (MODE == VKGSB_BLEND_FP32_MODE) {

@@ -8,12 +8,16 @@
 namespace vkgsb {
 
 constexpr int kTile = 16;              // origin granularity of the pinned fragment arithmetic (oracle: TILE = 16)
-// Binning granularity: one CTA of the blend stage owns a kBinW x kBinH pixel bin and splits it into 32 sub-tiles of
-// kSubW x kSubH pixels, one per warp (4 pixels per lane).
+// Two-level binning.  The sorted splat list is split ONCE into coarse bins (FrameParams::cshift_*: 128x128 pixels,
+// widened on the host until the image has at most kMaxCoarseBins of them, so the split is a single 8-bit radix pass);
+// one CTA of the blend stage owns a kBinW x kBinH pixel bin, streams the list of the coarse bin it lies in, keeps the
+// entries whose pixel box touches it and refines them to 32 sub-tiles of kSubW x kSubH pixels, one per warp
+// (4 pixels per lane).
 constexpr int kBinW = 64, kBinH = 64, kSubW = 16, kSubH = 8;
 constexpr uint32_t kFlagKeepInstances = 1u;  // also write the reference-format instance records (parity tap)
 constexpr int kSubCols = kBinW / kSubW, kSubRows = kBinH / kSubH;  // 4 x 8 = 32 sub-tiles
-constexpr int kMaxBins = 4096;  // 64 x 64 bins of 64 x 64 px: up to 4096 x 4096 images
+constexpr int kMaxCoarseBins = 256;
+constexpr int kMaxImageDim = 8192;
 static_assert(kSubCols * kSubRows == 32, "one sub-tile per warp of a 1024-thread CTA");
 constexpr int VKGSB_BLEND_FP32_MODE = 0, VKGSB_BLEND_UNORM8_MODE = 1;  // == enum vkgsb_blend_mode (include/vkgsb.h)
 
@@ -49,6 +53,11 @@ struct FrameParams {
   uint32_t bins_x, bins_y;    // bin grid of the whole image
   uint32_t band_y0, band_y1;  // rows [y0,y1) this renderer bins and blends
   uint32_t bin_y0, bin_y1;    // bin rows covering the band
+  uint32_t cshift_x, cshift_y;  // log2 of the coarse bin's width / height in pixels
+  uint32_t cbins_x;             // coarse bins per row
+  uint32_t cbin_y0;             // first coarse row of the band
+  uint32_t ncbins;              // coarse bins covering the band: cbins_x * rows (<= kMaxCoarseBins)
+  uint32_t pad1[3];
 };
 
 // ---- control block: everything the host zeroes with one memset per frame --------------------------------------
@@ -57,12 +66,12 @@ struct Control {
   uint32_t pair_count;      // D
   uint32_t pair_overflow;
   uint32_t project_ticket;
-  uint32_t pairs_ticket;
-  uint32_t sort_ticket[8];  // [0..3] depth passes, [4..7] tile passes
-  uint32_t pad[3];
+  uint32_t tile_cut;        // binning tiles [0, tile_cut) fit in max_pairs (bin.cu)
+  uint32_t bin_cost;        // total cost units of the kept tiles
+  uint32_t bin_items;       // work items of k_bin_count / k_bin_place
+  uint32_t sort_ticket[4];  // depth passes
+  uint32_t pad[1];
   uint32_t hist_depth[4 * 256];
-  uint32_t hist_bin[4 * 256];
-  uint32_t bin_count[kMaxBins];  // (bin, splat) pairs per bin, accumulated by k_make_pairs
 };
 
 // ---- decoupled look-back descriptor for the two ordered block scans (visible slots, pair offsets) --------------

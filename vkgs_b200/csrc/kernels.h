@@ -29,8 +29,8 @@ uint32_t project_num_blocks(uint32_t n);
 // d_rrec: 3 x float4 raster record per visible slot; d_inst: 12-float instance record (written only when
 // FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control.
 void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl, unsigned long long* d_scan_desc,
-                    uint32_t* d_keys, uint32_t* d_slots, uint32_t* d_vis_id, float* d_rrec, float* d_inst,
-                    cudaStream_t stream);
+                    uint32_t* d_keys, uint32_t* d_slots, uint32_t* d_vis_id, float* d_rrec, uint32_t* d_bin_rect,
+                    float* d_inst, cudaStream_t stream);
 
 // ---- sort.cu: onesweep LSD radix sort, count read on the device ----------------------------------------------------
 struct SortArgs {
@@ -46,22 +46,30 @@ struct SortArgs {
                             // caller when have_hist
   bool have_hist;           // the producer of the keys already built the digit histograms: no histogram pass
   int begin_bit;            // first pass digit starts here; passes are 8 bits wide
-  int npass;                // 2 or 4
+  int npass;                // 1, 2 or 4; odd: the result is in keys_alt / vals_alt
+  bool values_only;         // the caller only reads the sorted values: the last pass does not store keys
 };
 uint32_t sort_max_parts(uint32_t max_n);
 size_t sort_lookback_bytes(uint32_t max_n, int npass);
 void launch_sort(const SortArgs& a, cudaStream_t stream);
 
-// ---- bin.cu: (bin, slot) pairs in front-to-back order, per-bin ranges and digit histograms ------------------------
-uint32_t pairs_num_blocks(uint32_t max_visible);
-void launch_make_pairs(const FrameParams* d_fp, Control* d_ctrl, unsigned long long* d_scan_desc,
-                       const uint32_t* d_sorted_slots, const float* d_rrec, uint32_t max_visible, uint64_t max_pairs,
-                       uint32_t* d_pair_bin, uint32_t* d_pair_slot, cudaStream_t stream);
-void launch_bin_scan(const FrameParams* d_fp, Control* d_ctrl, uint2* d_ranges, uint32_t* d_lookback, uint64_t max_pairs,
-                     int npass, cudaStream_t stream);
+// ---- bin.cu: the sorted list split into one nearest-first list of splat slots per coarse bin ------------------------
+uint32_t bin_num_tiles(uint32_t max_visible);                      // tiles of 1024 sorted ranks
+uint32_t bin_max_items(uint32_t max_visible, uint64_t max_pairs);  // upper bound of the pair-balanced work items
+struct BinScratch {
+  uint32_t* tile_pairs;  // [tiles]
+  uint32_t* tile_cost;   // [tiles + 1]
+  uint32_t* item_bin;    // [kMaxCoarseBins][item_stride]
+  uint32_t* bin_total;   // [kMaxCoarseBins]
+  uint32_t item_stride;  // >= bin_max_items(max_visible, max_pairs) of every launch
+};
+void launch_bin(const FrameParams* d_fp, uint32_t ncbins, Control* d_ctrl, const uint32_t* d_sorted_slots,
+                const uint32_t* d_bin_rect, uint32_t max_visible, uint64_t max_pairs, const BinScratch& scratch,
+                uint2* d_ranges, uint32_t* d_bin_slots, cudaStream_t stream);
 
 // ---- blend.cu ------------------------------------------------------------------------------------------------------
 void blend_configure();  // once per device: opt in to > 48 KB dynamic shared memory
+// d_ranges: [begin,end) of every coarse bin in d_pair_slot
 void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_slot,
                   const float* d_rrec, int blend_mode, int bgra, uint8_t* d_image, cudaStream_t stream);
 

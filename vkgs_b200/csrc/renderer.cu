@@ -59,13 +59,15 @@ struct vkgsb_renderer {
   // per-frame work buffers
   uint32_t *keys = nullptr, *slots = nullptr, *keys_alt = nullptr, *slots_alt = nullptr, *vis_id = nullptr;
   float* inst = nullptr;
-  float* rrec = nullptr;  // raster records by front-to-back rank (bin.cu)
-  uint32_t *pair_bin = nullptr, *pair_slot = nullptr, *pair_bin_alt = nullptr, *pair_slot_alt = nullptr;
-  uint32_t *lookback_depth = nullptr, *lookback_bin = nullptr;
-  uint8_t* zero_region = nullptr;  // Control | scan descriptors (project) | scan descriptors (pairs) | tile ranges
+  float* rrec = nullptr;       // raster records by compacted slot (project.cu)
+  uint32_t* bin_rect = nullptr;  // coarse-bin box by compacted slot
+  uint32_t* bin_slots = nullptr;   // splat slots by coarse bin, nearest first (bin.cu); capacity max_pairs
+  BinScratch bin{};
+  uint32_t* lookback_depth = nullptr;
+  uint8_t* zero_region = nullptr;  // Control | scan descriptors (project) | coarse-bin ranges
   size_t zero_bytes = 0;
   Control* ctrl = nullptr;
-  unsigned long long *desc_project = nullptr, *desc_pairs = nullptr;
+  unsigned long long* desc_project = nullptr;
   uint2* ranges = nullptr;
   FrameParams* d_fp = nullptr;
   uint8_t* image = nullptr;
@@ -251,6 +253,20 @@ void fill_params(vkgsb_renderer* r) {
   p.bin_y0 = p.band_y0 / kBinH;
   p.bin_y1 = (p.band_y1 + kBinH - 1) / kBinH;
   if (p.band_y1 == p.band_y0) p.bin_y1 = p.bin_y0;
+  // coarse bins: 128 x 128 pixels, widened (x first) until the band has at most kMaxCoarseBins of them
+  p.cshift_x = p.cshift_y = 7;
+  auto coarse = [&](uint32_t* rows) {
+    p.cbins_x = ((r->width - 1) >> p.cshift_x) + 1;
+    p.cbin_y0 = p.band_y0 >> p.cshift_y;
+    *rows = p.band_y1 > p.band_y0 ? ((p.band_y1 - 1) >> p.cshift_y) - p.cbin_y0 + 1 : 0;
+    return p.cbins_x * *rows;
+  };
+  uint32_t crows = 0;
+  while (coarse(&crows) > static_cast<uint32_t>(kMaxCoarseBins)) {
+    if (p.cshift_x <= p.cshift_y) ++p.cshift_x; else ++p.cshift_y;
+  }
+  p.ncbins = p.cbins_x * crows;
+  p.pad1[0] = p.pad1[1] = p.pad1[2] = 0u;
 }
 
 // Stage kernels of one frame on `s`.  With `timed`, CUDA events bracket the stages (ev[0..4]).
@@ -261,7 +277,7 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   // look-back words of the depth sort: only partitions of the <= n visible splats can be touched
   CU_TRY(cudaMemsetAsync(r->lookback_depth, 0, sort_lookback_bytes(n, 4), s));
   if (timed) CU_TRY(cudaEventRecord(r->ev[0], s));
-  launch_project(sc, r->d_fp, r->ctrl, r->desc_project, r->keys, r->slots, r->vis_id, r->rrec, r->inst, s);
+  launch_project(sc, r->d_fp, r->ctrl, r->desc_project, r->keys, r->slots, r->vis_id, r->rrec, r->bin_rect, r->inst, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
   SortArgs depth{};
   depth.d_count = &r->ctrl->visible_count;
@@ -272,22 +288,9 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   depth.have_hist = true;  // k_project accumulated the four digit histograms
   launch_sort(depth, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[2], s));
-  launch_make_pairs(r->d_fp, r->ctrl, r->desc_pairs, r->slots, r->rrec, n, r->max_pairs, r->pair_bin, r->pair_slot, s);
-  const uint32_t nbins = r->h_fp.bins_x * (r->h_fp.bin_y1 - r->h_fp.bin_y0);
-  SortArgs bins{};
-  bins.d_count = &r->ctrl->pair_count;
-  bins.max_n = static_cast<uint32_t>(r->max_pairs);
-  bins.keys = r->pair_bin; bins.vals = r->pair_slot; bins.keys_alt = r->pair_bin_alt; bins.vals_alt = r->pair_slot_alt;
-  bins.hist = r->ctrl->hist_bin; bins.tickets = r->ctrl->sort_ticket + 4; bins.lookback = r->lookback_bin;
-  bins.begin_bit = 0;
-  bins.npass = nbins <= 256 ? 1 : 2;  // bin ids < 4096
-  bins.have_hist = true;              // k_bin_scan derives them from the per-bin counts
-  launch_bin_scan(r->d_fp, r->ctrl, r->ranges, r->lookback_bin, r->max_pairs, bins.npass, s);
-  launch_sort(bins, s);
-  // an odd pass count leaves the sorted pairs in the ping-pong buffers
-  const uint32_t* sorted_slot = (bins.npass & 1) ? r->pair_slot_alt : r->pair_slot;
+  launch_bin(r->d_fp, r->h_fp.ncbins, r->ctrl, r->slots, r->bin_rect, n, r->max_pairs, r->bin, r->ranges, r->bin_slots, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[3], s));
-  launch_blend(r->d_fp, r->h_fp, r->ranges, sorted_slot, r->rrec, r->blend_mode,
+  launch_blend(r->d_fp, r->h_fp, r->ranges, r->bin_slots, r->rrec, r->blend_mode,
                r->pixel_format == VKGSB_FORMAT_BGRA8, r->image, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[4], s));
   CU_TRY(cudaMemcpyAsync(r->h_counts, r->ctrl, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -392,18 +395,21 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   ALLOC(r->vis_id, N * 4);
   ALLOC(r->inst, N * 48);
   ALLOC(r->rrec, N * 48);
-  ALLOC(r->pair_bin, P * 4); ALLOC(r->pair_slot, P * 4); ALLOC(r->pair_bin_alt, P * 4); ALLOC(r->pair_slot_alt, P * 4);
+  ALLOC(r->bin_rect, N * 4);
+  ALLOC(r->bin_slots, P * 4);
+  r->bin.item_stride = bin_max_items(r->max_splats, r->max_pairs);
+  ALLOC(r->bin.tile_pairs, static_cast<size_t>(bin_num_tiles(r->max_splats)) * 4);
+  ALLOC(r->bin.tile_cost, (static_cast<size_t>(bin_num_tiles(r->max_splats)) + 1) * 4);
+  ALLOC(r->bin.item_bin, static_cast<size_t>(kMaxCoarseBins) * r->bin.item_stride * 4);
+  ALLOC(r->bin.bin_total, kMaxCoarseBins * 4);
   ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats, 4));
-  ALLOC(r->lookback_bin, sort_lookback_bytes(static_cast<uint32_t>(P), 2));
-  const size_t max_tiles = static_cast<size_t>((r->max_width + kBinW - 1) / kBinW) * ((r->max_height + kBinH - 1) / kBinH);
-  const size_t nb_proj = project_num_blocks(r->max_splats), nb_pairs = pairs_num_blocks(r->max_splats);
+  const size_t nb_proj = project_num_blocks(r->max_splats);
   const size_t ctrl_bytes = (sizeof(Control) + 255) & ~size_t(255);
-  r->zero_bytes = ctrl_bytes + (nb_proj + nb_pairs) * 8 + max_tiles * sizeof(uint2);
+  r->zero_bytes = ctrl_bytes + nb_proj * 8 + kMaxCoarseBins * sizeof(uint2);
   ALLOC(r->zero_region, r->zero_bytes);
   r->ctrl = reinterpret_cast<Control*>(r->zero_region);
   r->desc_project = reinterpret_cast<unsigned long long*>(r->zero_region + ctrl_bytes);
-  r->desc_pairs = r->desc_project + nb_proj;
-  r->ranges = reinterpret_cast<uint2*>(r->desc_pairs + nb_pairs);
+  r->ranges = reinterpret_cast<uint2*>(r->desc_project + nb_proj);
   ALLOC(r->d_fp, sizeof(FrameParams));
   ALLOC(r->image, static_cast<size_t>(r->max_width) * r->max_height * 4);
   ALLOC(r->d_offsets, 60 * 4);
@@ -436,8 +442,8 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   if (r->load_stream) cudaStreamSynchronize(r->load_stream);
   if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
   void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
-                 r->vis_id, r->inst, r->rrec, r->pair_bin, r->pair_slot, r->pair_bin_alt, r->pair_slot_alt, r->lookback_depth,
-                 r->lookback_bin, r->zero_region, r->d_fp, r->image, r->d_offsets, r->d_rows[0], r->d_rows[1]};
+                 r->vis_id, r->inst, r->rrec, r->bin_rect, r->bin_slots, r->bin.tile_pairs, r->bin.tile_cost, r->bin.item_bin, r->bin.bin_total,
+                 r->lookback_depth, r->zero_region, r->d_fp, r->image, r->d_offsets, r->d_rows[0], r->d_rows[1]};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (r->h_counts) cudaFreeHost(r->h_counts);
@@ -541,7 +547,7 @@ int vkgsb_set_viewport(vkgsb_renderer* r, uint32_t width, uint32_t height) {
   if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
   if (width == 0 || height == 0) return fail(VKGSB_ERR_INVALID, "empty viewport");
   if (static_cast<size_t>(width) * height > static_cast<size_t>(r->max_width) * r->max_height ||
-      (width + kBinW - 1) / kBinW > 64 || (height + kBinH - 1) / kBinH > 64)
+      width > static_cast<uint32_t>(kMaxImageDim) || height > static_cast<uint32_t>(kMaxImageDim))
     return fail(VKGSB_ERR_CAPACITY, "viewport larger than the renderer was created for");
   if (width != r->width || height != r->height) {
     std::lock_guard<std::mutex> g(r->draw_mutex);

@@ -15,6 +15,7 @@ constexpr int kSortThreads = 256;  // == radix: thread d owns digit d in the sca
 constexpr int kSortItems = 16;
 constexpr int kSortPart = kSortThreads * kSortItems;  // 4096 pairs per partition (PARTITION_SIZE, constants.slang:5)
 constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kLookBatch = 8;
 constexpr uint32_t kFlagAggregate = 1u << 30, kFlagInclusive = 2u << 30, kFlagMask = 3u << 30, kValueMask = ~kFlagMask;
 
 __host__ __device__ inline uint32_t parts_of(uint32_t n) { return (n + kSortPart - 1) / kSortPart; }
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int 
   uint32_t* __restrict__ dst_k = (pass & 1) ? a.keys : a.keys_alt;
   uint32_t* __restrict__ dst_v = (pass & 1) ? a.vals : a.vals_alt;
   uint32_t* __restrict__ lookback = a.lookback + static_cast<size_t>(pass) * max_parts * 256;
+  const bool store_keys = !(a.values_only && pass == a.npass - 1);
 
   // exclusive scan of this pass's global histogram (every block recomputes it: 256 words)
   uint32_t gexcl;
@@ -169,13 +171,27 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int 
         st_relaxed(mine, kFlagInclusive | total);
       } else {
         st_relaxed(mine, kFlagAggregate | total);
+        // Walk back kLookBatch predecessors per round trip: when the whole input is one wave of partitions (a 2 M-key
+        // depth sort is 500 of them) every aggregate appears at about the same time and a one-at-a-time walk would
+        // serialise hundreds of L2 latencies.
         int64_t q = static_cast<int64_t>(part) - 1;
-        while (true) {
-          uint32_t w = ld_relaxed(lookback + static_cast<size_t>(q) * 256 + tid);
-          if ((w & kFlagMask) == 0u) continue;
-          excl += w & kValueMask;
-          if ((w & kFlagMask) == kFlagInclusive) break;
-          --q;
+        bool fin = false;
+        while (!fin) {
+          uint32_t w[kLookBatch];
+#pragma unroll
+          for (int j = 0; j < kLookBatch; ++j)
+            w[j] = (q - j >= 0) ? ld_relaxed(lookback + static_cast<size_t>(q - j) * 256 + tid) : kFlagInclusive;
+          int used = 0;
+#pragma unroll
+          for (int j = 0; j < kLookBatch; ++j) {
+            const uint32_t f = w[j] & kFlagMask;
+            if (!fin && used == j && f != 0u) {
+              excl += w[j] & kValueMask;
+              used = j + 1;
+              fin = f == kFlagInclusive;
+            }
+          }
+          q -= used;
         }
         st_relaxed(mine, kFlagInclusive | (excl + total));
       }
@@ -219,7 +235,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int 
       const uint32_t j = i * kSortThreads + tid;
       if (j < valid) {
         const uint32_t k = s_keys[j];
-        dst_k[s_gbase[(k >> shift) & 255u] + j] = k;
+        if (store_keys) dst_k[s_gbase[(k >> shift) & 255u] + j] = k;
       }
     }
 #pragma unroll
