@@ -80,7 +80,8 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
     fly[k] = static_cast<float>(y - org_y);
     inside[k] = x < width && y >= band_y0 && y < band_y1;
   }
-  const uint2 range = ranges[((bin_y >> fpp->cshift_y) - fpp->cbin_y0) * fpp->cbins_x + (bin_x >> fpp->cshift_x)];
+  uint2 range = ranges[((bin_y >> fpp->cshift_y) - fpp->cbin_y0) * fpp->cbins_x + (bin_x >> fpp->cshift_x)];
+  if (range.y < range.x) range.y = range.x;  // a bin no pair reached keeps end = 0 (bin.cu)
   const uint32_t wbit = 1u << warp;
 
   if (MODE == VKGSB_BLEND_FP32_MODE) {

@@ -67,7 +67,7 @@ struct Control {
   uint32_t pair_overflow;
   uint32_t project_ticket;
   uint32_t tile_cut;        // binning tiles [0, tile_cut) fit in max_pairs (bin.cu)
-  uint32_t bin_cost;        // total cost units of the kept tiles
+  uint32_t partial_pairs;   // pairs kept of the last kept tile when the capacity cut falls inside it
   uint32_t bin_items;       // work items of k_bin_count / k_bin_place
   uint32_t sort_ticket[4];  // depth passes
   uint32_t pad[1];

@@ -56,13 +56,15 @@ void launch_sort(const SortArgs& a, cudaStream_t stream);
 // ---- bin.cu: the sorted list split into one nearest-first list of splat slots per coarse bin ------------------------
 uint32_t bin_num_tiles(uint32_t max_visible);                      // tiles of 1024 sorted ranks
 uint32_t bin_max_items(uint32_t max_visible, uint64_t max_pairs);  // upper bound of the pair-balanced work items
+size_t bin_slots_capacity(uint64_t max_pairs);                     // entries d_bin_slots must hold
 struct BinScratch {
-  uint32_t* tile_pairs;  // [tiles]
-  uint32_t* tile_cost;   // [tiles + 1]
-  uint32_t* item_bin;    // [kMaxCoarseBins][item_stride]
+  uint32_t* tile_pairs;  // [tile_stride]
+  uint32_t* tile_item;   // [tile_stride + 1]
+  uint32_t* tile_bin;    // [kMaxCoarseBins][tile_stride]
   uint32_t* bin_total;   // [kMaxCoarseBins]
-  uint32_t item_stride;  // >= bin_max_items(max_visible, max_pairs) of every launch
+  uint32_t tile_stride;  // >= bin_num_tiles(max_visible) of every launch
 };
+// d_ranges[b] = [begin, end) of coarse bin b in d_bin_slots (end <= begin: empty); must be zero on entry.
 void launch_bin(const FrameParams* d_fp, uint32_t ncbins, Control* d_ctrl, const uint32_t* d_sorted_slots,
                 const uint32_t* d_bin_rect, uint32_t max_visible, uint64_t max_pairs, const BinScratch& scratch,
                 uint2* d_ranges, uint32_t* d_bin_slots, cudaStream_t stream);

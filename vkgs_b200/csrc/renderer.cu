@@ -396,11 +396,11 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   ALLOC(r->inst, N * 48);
   ALLOC(r->rrec, N * 48);
   ALLOC(r->bin_rect, N * 4);
-  ALLOC(r->bin_slots, P * 4);
-  r->bin.item_stride = bin_max_items(r->max_splats, r->max_pairs);
-  ALLOC(r->bin.tile_pairs, static_cast<size_t>(bin_num_tiles(r->max_splats)) * 4);
-  ALLOC(r->bin.tile_cost, (static_cast<size_t>(bin_num_tiles(r->max_splats)) + 1) * 4);
-  ALLOC(r->bin.item_bin, static_cast<size_t>(kMaxCoarseBins) * r->bin.item_stride * 4);
+  ALLOC(r->bin_slots, bin_slots_capacity(P) * 4);
+  r->bin.tile_stride = bin_num_tiles(r->max_splats);
+  ALLOC(r->bin.tile_pairs, static_cast<size_t>(r->bin.tile_stride) * 4);
+  ALLOC(r->bin.tile_item, (static_cast<size_t>(r->bin.tile_stride) + 1) * 4);
+  ALLOC(r->bin.tile_bin, static_cast<size_t>(kMaxCoarseBins) * r->bin.tile_stride * 4);
   ALLOC(r->bin.bin_total, kMaxCoarseBins * 4);
   ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats, 4));
   const size_t nb_proj = project_num_blocks(r->max_splats);
@@ -442,7 +442,7 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   if (r->load_stream) cudaStreamSynchronize(r->load_stream);
   if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
   void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
-                 r->vis_id, r->inst, r->rrec, r->bin_rect, r->bin_slots, r->bin.tile_pairs, r->bin.tile_cost, r->bin.item_bin, r->bin.bin_total,
+                 r->vis_id, r->inst, r->rrec, r->bin_rect, r->bin_slots, r->bin.tile_pairs, r->bin.tile_item, r->bin.tile_bin, r->bin.bin_total,
                  r->lookback_depth, r->zero_region, r->d_fp, r->image, r->d_offsets, r->d_rows[0], r->d_rows[1]};
   for (void* p : dev)
     if (p) cudaFree(p);
