@@ -255,64 +255,73 @@ typedef struct {
   uint32_t width, height;
 } vko_camera;
 
-/* One splat of projection.comp:77-179.  variant 0 = pinned half-angle (sqrt/div only,
- * bit-exact on any IEEE device); variant 1 = the literal atan/cos/sin of
- * projection.comp:130-132 through libm (cross-check of the restatement). */
-static void project_one(const vko_camera* cam, const float* cam_m, const float* pos3, const float* cov6,
+/* Per-frame constants of the projection, hoisted out of the per-splat work exactly as the CUDA path's FrameParams
+ * carries them (renderer.cu fill_params): products of the camera matrices and reciprocals of the viewport size. */
+typedef struct {
+  float vm[16];   /* view * model                                   (projection.comp:98-102 composed) */
+  float w3[9];    /* mat3(view) * mat3(model), column-major m[c*3+r]  (:95-101 composed)               */
+  float ps[4];    /* mat2(projection), column-major m[c*2+r]          (:112)                           */
+  float lpx, lpy; /* 1/W/W, 1/H/H                                     (:116-117)                       */
+  float cam_m[3]; /* inverse(model) * eye / w                         (:85-86)                         */
+} vko_frame;
+
+static void frame_setup(const vko_camera* cam, vko_frame* f) {
+  float m3[9], v3[9];
+  mat4_mul(cam->view, cam->model, f->vm);
+  mat3_of_mat4(cam->model, m3);
+  mat3_of_mat4(cam->view, v3);
+  mat3_mul(v3, m3, f->w3);
+  f->ps[0] = cam->proj[0]; f->ps[1] = cam->proj[1]; f->ps[2] = cam->proj[4]; f->ps[3] = cam->proj[5];
+  float fw = (float)cam->width, fh = (float)cam->height;
+  f->lpx = 1.f / fw / fw;
+  f->lpy = 1.f / fh / fh;
+  vko_camera_in_model(cam->model, cam->eye, f->cam_m);
+}
+
+/* One splat of projection.comp:77-179, restated with the frame-constant matrix products hoisted and every division
+ * by a shared denominator turned into ONE IEEE reciprocal and multiplications (the GLSL leaves both the association
+ * of its matrix products' roundings and `a / b` vs `a * (1/b)` to the driver; this is the order both this file and the
+ * CUDA kernel commit to, bit for bit).  With W = mat3(view)*mat3(model), t = (view*model)*pos and the first two rows
+ * of J (the third never reaches cov2d), cov2d = K * Sigma * K^T for the 2x3 matrix K = mat2(proj) * J * W.
+ * variant 0 = pinned half-angle (sqrt/div only, bit-exact on any IEEE device); variant 1 = the literal atan/cos/sin
+ * of projection.comp:130-132 through libm (cross-check of the restatement). */
+static void project_one(const vko_camera* cam, const vko_frame* f, const float* pos3, const float* cov6,
                         float opac, const uint16_t* sh48, int variant, float* inst) {
   /* dir = normalize(pos - cam_model)   projection.comp:87 */
-  float dx = pos3[0] - cam_m[0], dy = pos3[1] - cam_m[1], dz = pos3[2] - cam_m[2];
-  float dl = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-  float x = dx / dl, y = dy / dl, z = dz / dl;
+  float dx = pos3[0] - f->cam_m[0], dy = pos3[1] - f->cam_m[1], dz = pos3[2] - f->cam_m[2];
+  float il = 1.f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+  float x = dx * il, y = dy * il, z = dz * il;
 
-  /* cov3d = mat3(v0, v0.y, v1.xy, v0.z, v1.yz)   projection.comp:92 */
-  float c3[9] = {cov6[0], cov6[1], cov6[2], cov6[1], cov6[3], cov6[4], cov6[2], cov6[4], cov6[5]};
-  float m3[9], t3[9], p4[4] = {pos3[0], pos3[1], pos3[2], 1.f}, pm[4], pv[4];
-  mat3_of_mat4(cam->model, m3); /* :95-97 */
-  mat3_mul(m3, c3, c3);
-  mat3_transpose(m3, t3);
-  mat3_mul(c3, t3, c3);
-  mat4_vec(cam->model, p4, pm);
-  mat3_of_mat4(cam->view, m3); /* :100-102 */
-  mat3_mul(m3, c3, c3);
-  mat3_transpose(m3, t3);
-  mat3_mul(c3, t3, c3);
-  mat4_vec(cam->view, pm, pv);
-
-  /* projection.comp:105-109 */
+  /* t = view * model * pos   :98,102 */
+  float p4[4] = {pos3[0], pos3[1], pos3[2], 1.f}, pv[4];
+  mat4_vec(f->vm, p4, pv);
   float px = pv[0], py = pv[1], pz = pv[2];
-  float r = sqrtf(fmaf(pz, pz, fmaf(py, py, px * px)));
-  float J[9] = {-1.f / pz, 0.f, -2.f * px / r, 0.f, -1.f / pz, -2.f * py / r, px / pz / pz, py / pz / pz, -2.f * pz / r};
-  /* cov3d = J * cov3d * transpose(J); only its upper-left 2x2 is read afterwards (mat2(cov3d), :112), so only the
-   * elements that feed it are evaluated - each by the same chain the full product would use. */
-  {
-    float T[9]; /* T = J * cov3d, rows 0 and 1 */
-    for (int cc = 0; cc < 3; ++cc)
-      for (int rr = 0; rr < 2; ++rr)
-        T[cc * 3 + rr] = fmaf(J[2 * 3 + rr], c3[cc * 3 + 2], fmaf(J[1 * 3 + rr], c3[cc * 3 + 1], J[0 * 3 + rr] * c3[cc * 3 + 0]));
-    for (int cc = 0; cc < 2; ++cc)   /* (T * J^T)[cc][rr] = sum_k T[k][rr] * J[k][cc] */
-      for (int rr = 0; rr < 2; ++rr)
-        c3[cc * 3 + rr] = fmaf(T[2 * 3 + rr], J[2 * 3 + cc], fmaf(T[1 * 3 + rr], J[1 * 3 + cc], T[0 * 3 + rr] * J[0 * 3 + cc]));
-  }
 
-  /* cov2d = mat2(proj) * mat2(cov3d) * mat2(proj)   :112-113; 2x2 column-major m[c*2+r] */
-  float ps[4] = {cam->proj[0], cam->proj[1], cam->proj[4], cam->proj[5]};
-  float c2[4] = {c3[0], c3[1], c3[3], c3[4]}, t2[4], cov2d[4];
-  for (int c = 0; c < 2; ++c)
-    for (int rr = 0; rr < 2; ++rr) t2[c * 2 + rr] = fmaf(ps[1 * 2 + rr], c2[c * 2 + 1], ps[0 * 2 + rr] * c2[c * 2 + 0]);
-  for (int c = 0; c < 2; ++c)
-    for (int rr = 0; rr < 2; ++rr) cov2d[c * 2 + rr] = fmaf(t2[1 * 2 + rr], ps[c * 2 + 1], t2[0 * 2 + rr] * ps[c * 2 + 0]);
-  /* low-pass   :116-117 */
-  float fw = (float)cam->width, fh = (float)cam->height;
-  cov2d[0] = cov2d[0] + 1.f / fw / fw;
-  cov2d[3] = cov2d[3] + 1.f / fh / fh;
+  /* rows 0 and 1 of J (:105-108): (-1/z, 0, x/z/z), (0, -1/z, y/z/z); PJ = mat2(proj) * J, 2x3, PJ[r][c] */
+  float iz = 1.f / pz, niz = -iz;
+  float j02 = (px * iz) * iz, j12 = (py * iz) * iz;
+  float P00 = f->ps[0], P10 = f->ps[1], P01 = f->ps[2], P11 = f->ps[3]; /* P[r][c] = ps[c*2+r] */
+  float PJ[2][3] = {{P00 * niz, P01 * niz, fmaf(P01, j12, P00 * j02)}, {P10 * niz, P11 * niz, fmaf(P11, j12, P10 * j02)}};
+  /* K = PJ * W,  K[r][c] = sum_k PJ[r][k] * W[k][c],  W[k][c] = w3[c*3+k] */
+  float K[2][3], M[2][3];
+  for (int r = 0; r < 2; ++r)
+    for (int c = 0; c < 3; ++c)
+      K[r][c] = fmaf(PJ[r][2], f->w3[c * 3 + 2], fmaf(PJ[r][1], f->w3[c * 3 + 1], PJ[r][0] * f->w3[c * 3 + 0]));
+  /* M = K * Sigma,  Sigma = mat3(v0, v0.y, v1.xy, v0.z, v1.yz) symmetric   :92 */
+  float S[3][3] = {{cov6[0], cov6[1], cov6[2]}, {cov6[1], cov6[3], cov6[4]}, {cov6[2], cov6[4], cov6[5]}};
+  for (int r = 0; r < 2; ++r)
+    for (int c = 0; c < 3; ++c) M[r][c] = fmaf(K[r][2], S[2][c], fmaf(K[r][1], S[1][c], K[r][0] * S[0][c]));
+  /* cov2d = M * K^T + low-pass   :112-117;  a = [0][0], b = [1][1], c = [1][0] (column 1, row 0) */
+  float a = fmaf(M[0][2], K[0][2], fmaf(M[0][1], K[0][1], M[0][0] * K[0][0])) + f->lpx;
+  float b = fmaf(M[1][2], K[1][2], fmaf(M[1][1], K[1][1], M[1][0] * K[1][0])) + f->lpy;
+  float c = fmaf(M[0][2], K[1][2], fmaf(M[0][1], K[1][1], M[0][0] * K[1][0]));
 
   /* eigendecomposition   :122-134 */
-  float a = cov2d[0], b = cov2d[3], c = cov2d[2];
   float D = sqrtf(fmaf(4.f * c, c, (a - b) * (a - b)));
   float s0 = sqrtf(0.5f * ((a + b) + D));
   float s1 = sqrtf(0.5f * ((a + b) - D));
-  float sin2t = 2.f * c / D, cos2t = (a - b) / D;
+  float iD = 1.f / D;
+  float sin2t = (2.f * c) * iD, cos2t = (a - b) * iD;
   float ct, st;
   if (variant == 1) {
     float theta = atan2f(sin2t, cos2t) / 2.f;
@@ -328,7 +337,8 @@ static void project_one(const vko_camera* cam, const float* cam_m, const float* 
   /* pos = projection * pos; pos /= pos.w   :136-137 */
   float pc[4];
   mat4_vec(cam->proj, pv, pc);
-  float nx = pc[0] / pc[3], ny = pc[1] / pc[3], nz = pc[2] / pc[3];
+  float iw = 1.f / pc[3];
+  float nx = pc[0] * iw, ny = pc[1] * iw, nz = pc[2] * iw;
 
   /* SH degree 3   :140-174 */
   const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f, C20 = 1.0925484305920792f,
@@ -367,12 +377,12 @@ static void project_one(const vko_camera* cam, const float* cam_m, const float* 
 /* inst[i*12..] for i in [0,v): record of splat ids[i] (i.e. written at its sorted slot, :177-179). */
 VKO_API void vko_project(uint32_t v, const uint32_t* ids, const float* pos, const float* cov, const float* opacity,
                          const uint16_t* sh, const vko_camera* cam, int variant, float* inst) {
-  float cam_m[3];
-  vko_camera_in_model(cam->model, cam->eye, cam_m);
+  vko_frame f;
+  frame_setup(cam, &f);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)v; ++i) {
     uint64_t id = ids[i];
-    project_one(cam, cam_m, pos + 3 * id, cov + 6 * id, opacity[id], sh + 48 * id, variant, inst + 12 * i);
+    project_one(cam, &f, pos + 3 * id, cov + 6 * id, opacity[id], sh + 48 * id, variant, inst + 12 * i);
   }
 }
 
@@ -386,7 +396,7 @@ VKO_API void vko_project(uint32_t v, const uint32_t* ids, const float* pos, cons
  * Pinned per-fragment arithmetic (the Vulkan rasteriser's own interpolation is
  * implementation-defined; this is the restatement both sides share):
  *   hw = W/2, hh = H/2;  cpx = fma(ndc.x, hw, hw-0.5), cpy likewise    (pixel i centre <-> ndc (i+.5)*2/W-1)
- *   m = diag(hw,hh)*RS;  det = m00*m11 - m01*m10;  A = m^-1 = [m11,-m01;-m10,m00]/det
+ *   m = diag(hw,hh)*RS;  det = m00*m11 - m01*m10;  A = m^-1 = [m11,-m01;-m10,m00] * (1/det)
  *   per TILE-aligned origin (tx,ty):  ox = tx-cpx, oy = ty-cpy;  bx = A00*ox + A01*oy;  by = A10*ox + A11*oy
  *   per pixel (lx,ly) in tile:        px = fma(A00,lx,fma(A01,ly,bx));  py = fma(A10,lx,fma(A11,ly,by))
  *   covered <=> |px|<=3 && |py|<=3 && ndc.z<1;   alpha = opacity*exp(-0.5*(px*px+py*py))
@@ -408,7 +418,8 @@ static void raster_setup(const float* inst, uint32_t W, uint32_t H, raster_splat
   s->cpy = fmaf(inst[1], hh, hh - 0.5f);
   float m00 = inst[4] * hw, m10 = inst[5] * hh, m01 = inst[6] * hw, m11 = inst[7] * hh; /* m[r][c] */
   float det = m00 * m11 - m01 * m10;
-  s->a00 = m11 / det; s->a01 = -m01 / det; s->a10 = -m10 / det; s->a11 = m00 / det;
+  float idet = 1.f / det;
+  s->a00 = m11 * idet; s->a01 = -m01 * idet; s->a10 = -m10 * idet; s->a11 = m00 * idet;
   float cr = inst[8], cg = inst[9], cb = inst[10];
   s->r = cr < 0.f ? 0.f : (cr > 1.f ? 1.f : cr);
   s->g = cg < 0.f ? 0.f : (cg > 1.f ? 1.f : cg);

@@ -46,6 +46,11 @@ struct FrameParams {
   float view[16];
   float model[16];
   float pvm[16];        // (proj*view)*model composed on the host, rank.comp:32
+  float vm[16];         // view*model                        (projection.comp:98-102 composed on the host)
+  float w3[9];          // mat3(view)*mat3(model), m[c*3+r]  (projection.comp:95-101)
+  float ps[4];          // mat2(proj), m[c*2+r]              (projection.comp:112)
+  float lpx, lpy;       // 1/W/W, 1/H/H                      (projection.comp:116-117)
+  float pad2;
   float cam_model[3];   // inverse(model)*eye / w, projection.comp:85-86 hoisted
   uint32_t flags;       // kFlagKeepInstances
   uint32_t pad0;

@@ -25,7 +25,7 @@ void launch_export_scene(const SceneStorage& src, uint32_t n, float* d_pos, floa
                          uint16_t* d_sh, cudaStream_t stream);
 
 // ---- project.cu ------------------------------------------------------------------------------------------------
-uint32_t project_num_blocks(uint32_t n);
+uint32_t project_num_tiles(uint32_t n);  // scan descriptors k_project needs
 // d_rrec: 3 x float4 raster record per visible slot; d_inst: 12-float instance record (written only when
 // FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control.
 void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl, unsigned long long* d_scan_desc,

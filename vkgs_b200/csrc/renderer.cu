@@ -238,6 +238,16 @@ void fill_params(vkgsb_renderer* r) {
   float inv[16], e[4] = {r->cam.camera_position[0], r->cam.camera_position[1], r->cam.camera_position[2], 1.f}, cm[4];
   mat4_inverse(p.model, inv);  // inverse(model) * vec4(camera_position, 1), hoisted (projection.comp:85-86)
   mat4_vec(inv, e, cm);
+  mat4_mul(p.view, p.model, p.vm);
+  for (int c = 0; c < 3; ++c)
+    for (int rr = 0; rr < 3; ++rr)  // mat3(view) * mat3(model), same chain as the oracle's mat3_mul
+      p.w3[c * 3 + rr] = std::fmaf(p.view[2 * 4 + rr], p.model[c * 4 + 2],
+                                   std::fmaf(p.view[1 * 4 + rr], p.model[c * 4 + 1], p.view[0 * 4 + rr] * p.model[c * 4 + 0]));
+  p.ps[0] = p.proj[0]; p.ps[1] = p.proj[1]; p.ps[2] = p.proj[4]; p.ps[3] = p.proj[5];
+  const float fw = static_cast<float>(r->width), fh = static_cast<float>(r->height);
+  p.lpx = 1.f / fw / fw;
+  p.lpy = 1.f / fh / fh;
+  p.pad2 = 0.f;
   p.cam_model[0] = cm[0] / cm[3];
   p.cam_model[1] = cm[1] / cm[3];
   p.cam_model[2] = cm[2] / cm[3];
@@ -403,7 +413,7 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   ALLOC(r->bin.tile_bin, static_cast<size_t>(kMaxCoarseBins) * r->bin.tile_stride * 4);
   ALLOC(r->bin.bin_total, kMaxCoarseBins * 4);
   ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats, 4));
-  const size_t nb_proj = project_num_blocks(r->max_splats);
+  const size_t nb_proj = project_num_tiles(r->max_splats);
   const size_t ctrl_bytes = (sizeof(Control) + 255) & ~size_t(255);
   r->zero_bytes = ctrl_bytes + nb_proj * 8 + kMaxCoarseBins * sizeof(uint2);
   ALLOC(r->zero_region, r->zero_bytes);
