@@ -93,16 +93,18 @@ __device__ __forceinline__ unsigned long long scan_peek(const unsigned long long
   return w;
 }
 
-// Exclusive prefix of `block_total` over all blocks with a smaller ticket.  Call from ONE full warp (warp-uniform
-// ticket); every lane returns the prefix.  Publishes this block's aggregate, walks back 32 descriptors at a time,
-// then publishes the inclusive value.
-__device__ __forceinline__ uint32_t scan_lookback_warp(unsigned long long* desc, uint32_t ticket, uint32_t block_total) {
+// Ordered scan over ticketed tiles in two steps, so that a tile's aggregate can be published long before its prefix is
+// needed.  Both are called by ONE full warp with a warp-uniform ticket.
+//   scan_post(desc, ticket, total)     publish this tile's aggregate (tile 0: its inclusive value) - never waits.
+//   scan_resolve(desc, ticket, total)  exclusive prefix of `total` over all tiles with a smaller ticket: walks back 32
+//                                      descriptors at a time until one holds an inclusive value, then publishes this
+//                                      tile's inclusive value.  Every lane returns the prefix.
+__device__ __forceinline__ void scan_post(unsigned long long* desc, uint32_t ticket, uint32_t total) {
+  if ((threadIdx.x & 31u) == 0) scan_publish(desc + ticket, ticket == 0 ? kScanInclusive : kScanAggregate, total);
+}
+__device__ __forceinline__ uint32_t scan_resolve(unsigned long long* desc, uint32_t ticket, uint32_t total) {
   const uint32_t lane = threadIdx.x & 31u;
-  if (ticket == 0) {
-    if (lane == 0) scan_publish(desc, kScanInclusive, block_total);
-    return 0u;
-  }
-  if (lane == 0) scan_publish(desc + ticket, kScanAggregate, block_total);
+  if (ticket == 0) return 0u;
   uint32_t prefix = 0;
   int64_t hi = static_cast<int64_t>(ticket) - 1;  // newest descriptor not yet consumed
   while (true) {
@@ -119,7 +121,7 @@ __device__ __forceinline__ uint32_t scan_lookback_warp(unsigned long long* desc,
     }
     // first lane (nearest predecessor side) holding an inclusive value terminates the walk
     uint32_t incl_mask = __ballot_sync(0xffffffffu, st == kScanInclusive);
-    uint32_t first = __ffs(incl_mask) - 1;  // incl_mask != 0 guaranteed once idx < 0 lanes exist or found
+    uint32_t first = __ffs(incl_mask) - 1;
     if (incl_mask == 0u) first = 32u;
     uint32_t contrib = (lane <= first) ? val : 0u;
 #pragma unroll
@@ -128,8 +130,13 @@ __device__ __forceinline__ uint32_t scan_lookback_warp(unsigned long long* desc,
     if (incl_mask != 0u) break;
     hi -= 32;
   }
-  if (lane == 0) scan_publish(desc + ticket, kScanInclusive, prefix + block_total);
+  if (lane == 0) scan_publish(desc + ticket, kScanInclusive, prefix + total);
   return prefix;
+}
+// Both steps back to back.
+__device__ __forceinline__ uint32_t scan_lookback_warp(unsigned long long* desc, uint32_t ticket, uint32_t block_total) {
+  scan_post(desc, ticket, block_total);
+  return scan_resolve(desc, ticket, block_total);
 }
 
 }  // namespace vkgsb
