@@ -71,6 +71,10 @@ struct vkgsb_renderer {
   uint2* ranges = nullptr;
   FrameParams* d_fp = nullptr;
   uint8_t* image = nullptr;
+  // draw_batch to host memory: frame i is copied out of stage[i & 1] on copy_stream while frame i + 1 renders
+  uint8_t* stage[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t frame_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
   uint32_t* h_counts = nullptr;  // pinned: visible, pairs, overflow of the last frame
 
   // load staging
@@ -398,6 +402,11 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   if ((e = cudaSetDevice(r->device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&r->load_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaEventCreateWithFlags(&r->frame_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaEventCreateWithFlags(&r->copy_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+  }
   const size_t N = r->max_splats, P = r->max_pairs;
   ALLOC(r->scene.x, N * 4); ALLOC(r->scene.y, N * 4); ALLOC(r->scene.z, N * 4);
   ALLOC(r->scene.payload, N * sizeof(SplatPayload));
@@ -422,6 +431,8 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   r->ranges = reinterpret_cast<uint2*>(r->desc_project + nb_proj);
   ALLOC(r->d_fp, sizeof(FrameParams));
   ALLOC(r->image, static_cast<size_t>(r->max_width) * r->max_height * 4);
+  ALLOC(r->stage[0], static_cast<size_t>(r->max_width) * r->max_height * 4);
+  ALLOC(r->stage[1], static_cast<size_t>(r->max_width) * r->max_height * 4);
   ALLOC(r->d_offsets, 60 * 4);
 #undef ALLOC
   if ((e = cudaMallocHost(reinterpret_cast<void**>(&r->h_counts), 64)) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -453,7 +464,8 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
   void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
                  r->vis_id, r->inst, r->rrec, r->bin_rect, r->bin_slots, r->bin.tile_pairs, r->bin.tile_item, r->bin.tile_bin, r->bin.bin_total,
-                 r->lookback_depth, r->zero_region, r->d_fp, r->image, r->d_offsets, r->d_rows[0], r->d_rows[1]};
+                 r->lookback_depth, r->zero_region, r->d_fp, r->image, r->stage[0], r->stage[1], r->d_offsets, r->d_rows[0],
+                 r->d_rows[1]};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (r->h_counts) cudaFreeHost(r->h_counts);
@@ -463,8 +475,13 @@ void vkgsb_destroy(vkgsb_renderer* r) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : r->chunk_done)
     if (ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; ++i) {
+    if (r->frame_done[i]) cudaEventDestroy(r->frame_done[i]);
+    if (r->copy_done[i]) cudaEventDestroy(r->copy_done[i]);
+  }
   if (r->stream) cudaStreamDestroy(r->stream);
   if (r->load_stream) cudaStreamDestroy(r->load_stream);
+  if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
   delete r;
 }
 
@@ -590,15 +607,36 @@ int vkgsb_draw_batch(vkgsb_renderer* r, uint32_t n_views, const vkgsb_camera* ca
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : r->stream;
   const size_t bytes = static_cast<size_t>(r->width) * r->height * 4;
   if (dst && dst_stride < bytes) return fail(VKGSB_ERR_INVALID, "dst_stride smaller than one image");
+  if (dst && !dst_is_device) {
+    // Host destination: double-buffered.  The finished frame is parked in stage[i & 1] (a 2 us device copy) and leaves
+    // over PCIe on copy_stream while the next view renders; the render stream only waits for the copy that last read
+    // the stage it is about to overwrite.
+    bool used[2] = {false, false};
+    for (uint32_t i = 0; i < n_views; ++i) {
+      const int b = static_cast<int>(i & 1u);
+      r->cam = cameras[i];
+      r->have_cam = true;
+      if (int e = run_frame(r, s)) return e;
+      if (used[b]) CU_TRY(cudaStreamWaitEvent(s, r->copy_done[b], 0));
+      CU_TRY(cudaMemcpyAsync(r->stage[b], r->image, bytes, cudaMemcpyDeviceToDevice, s));
+      CU_TRY(cudaEventRecord(r->frame_done[b], s));
+      CU_TRY(cudaStreamWaitEvent(r->copy_stream, r->frame_done[b], 0));
+      CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + i * dst_stride, r->stage[b], bytes, cudaMemcpyDeviceToHost,
+                             r->copy_stream));
+      CU_TRY(cudaEventRecord(r->copy_done[b], r->copy_stream));
+      used[b] = true;
+    }
+    CU_TRY(cudaStreamSynchronize(r->copy_stream));  // returns when every image is in dst
+    CU_TRY(cudaStreamSynchronize(s));
+    return VKGSB_OK;
+  }
   for (uint32_t i = 0; i < n_views; ++i) {
     r->cam = cameras[i];
     r->have_cam = true;
     if (int e = run_frame(r, s)) return e;
     if (dst)
-      CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + i * dst_stride, r->image, bytes,
-                             dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + i * dst_stride, r->image, bytes, cudaMemcpyDeviceToDevice, s));
   }
-  if (dst && !dst_is_device) CU_TRY(cudaStreamSynchronize(s));
   return VKGSB_OK;
 }
 

@@ -133,6 +133,14 @@ class Renderer:
         L.check(L.lib().vkgsb_draw_batch(self._h, n, arr, _ptr(out), stride, 0, C.c_void_p(stream)))
         return out
 
+    def draw_batch_to_host_ptr(self, cameras, host_ptr: int, stream: int = 0):
+        """n views into host memory at host_ptr (n * width * height * 4 bytes, ideally pinned): frame i leaves over PCIe
+        while frame i + 1 renders; returns when every image has arrived."""
+        n = len(cameras)
+        arr = (L.CameraBlock * n)(*cameras)
+        L.check(L.lib().vkgsb_draw_batch(self._h, n, arr, C.c_void_p(host_ptr), self.width * self.height * 4, 0,
+                                         C.c_void_p(stream)))
+
     def image_device_ptr(self) -> int:
         p = C.c_void_p()
         L.check(L.lib().vkgsb_image_device_ptr(self._h, C.byref(p)))
