@@ -182,7 +182,8 @@ VKO_API void vko_camera_in_model(const float* model, const float* eye, float* ou
 static inline int cull_one(const float* pvm, const float* p3, uint32_t* key) {
   float v[4] = {p3[0], p3[1], p3[2], 1.f}, c[4];
   mat4_vec(pvm, v, c);
-  float x = c[0] / c[3], y = c[1] / c[3], z = c[2] / c[3]; /* pos / pos.w, rank.comp:33 */
+  float iw = 1.f / c[3]; /* pos / pos.w, rank.comp:33, pinned as one IEEE reciprocal and three products */
+  float x = c[0] * iw, y = c[1] * iw, z = c[2] * iw;
   if (fabsf(x) <= 1.f && fabsf(y) <= 1.f && z >= 0.f && z <= 1.f) { /* rank.comp:37 */
     *key = f2u(1.f - z);                                             /* rank.comp:39 */
     return 1;
