@@ -28,7 +28,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-I", os.path.join(ROOT, "include"),
 
 # source -> extra flags
 SOURCES = {
-    "project.cu": ["-fmad=false"],
+    "project.cu": ["-fmad=false"] + os.environ.get("VKGSB_PROJECT_FLAGS", "").split(),
     "load.cu": ["-fmad=false"],
     "sort.cu": [],
     "bin.cu": [],
