@@ -1,0 +1,110 @@
+"""N>1 host logic on CPU: two `gloo` ranks shard an orbit by view and one frame by screen band (SURVEY.md §8e,
+vkgs_b200/dist.py), gather to rank 0 and must reproduce the single-process result byte for byte.  The CPU oracle stands
+in for the renderer here (tests may use it as the checker's renderer; the product never does): what is under test is
+the sharding, the gather and the assembly, the very functions bench.py --gpus N and a band-sharded viewer call."""
+from __future__ import annotations
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle as O
+from vkgs_b200 import camera as pycam
+from vkgs_b200 import dist as vdist
+from vkgs_b200 import synth
+
+W, H, N_VIEWS, N_SPLATS = 160, 96, 5, 3000
+
+
+def _scene():
+    return O.activate(synth.scene_c1(n=N_SPLATS, seed=9), synth.STANDARD_OFFSETS)
+
+
+def _camera(i):
+    c = pycam.orbit(W, H, r=2.5, phi_deg=60.0, theta_deg=360.0 * i / N_VIEWS)
+    return c.projection_matrix(), c.view_matrix(), c.eye()
+
+
+def _render_view(scene, i):
+    P, V, E = _camera(i)
+    return O.render(scene, O.make_camera(P, V, E, W, H), mode=0)["image"]
+
+
+def _render_band(scene, i, y0, y1):
+    P, V, E = _camera(i)
+    cam = O.make_camera(P, V, E, W, H)
+    keys, ids = O.cull(scene, O.compose_pvm(P, V))
+    keys, ids = O.sort_pairs(keys, ids)
+    inst = O.project(scene, ids, cam, 0)
+    img = O.raster_rows(inst, W, H, y0, y1, mode=0)
+    img[:y0] = 0
+    img[y1:] = 0   # rows outside the band are not this rank's to deliver
+    return img
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        scene = _scene()
+        # ---- by view: contiguous camera blocks, padded to the largest block so the gather is rectangular
+        mine = vdist.shard_views(N_VIEWS, rank, world)
+        kmax = max(len(vdist.shard_views(N_VIEWS, r, world)) for r in range(world))
+        local = torch.zeros((kmax, H, W, 4), dtype=torch.uint8)
+        for j, i in enumerate(mine):
+            local[j] = torch.from_numpy(_render_view(scene, i))
+        got = vdist.gather_images(local, dst=0)
+        # ---- by band: one view, rank g owns rows [edges[g], edges[g+1])
+        edges = vdist.band_edges(H, world)
+        band = torch.from_numpy(_render_band(scene, 1, edges[rank], edges[rank + 1]))[None]
+        got_b = vdist.gather_images(band, dst=0)
+        slowest = vdist.max_over_ranks(float(rank + 1))
+        if rank == 0:
+            views = vdist.assemble_views(got, N_VIEWS).numpy()
+            frame = vdist.assemble_bands(got_b, edges).numpy()[0]
+            np.savez(out_path, views=views, frame=frame, slowest=slowest, edges=np.array(edges))
+        else:
+            assert got is None and got_b is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_views_partitions_the_orbit():
+    for n in (0, 1, 5, 64, 360):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [vdist.shard_views(n, r, world) for r in range(world)]
+            assert [i for b in blocks for i in b] == list(range(n))
+            assert max(len(b) for b in blocks) - min(len(b) for b in blocks) <= 1
+
+
+def test_band_edges_cover_the_frame_tile_aligned():
+    for h in (16, 96, 600, 900, 1080, 2160):
+        for world in (1, 2, 4, 8):
+            e = vdist.band_edges(h, world)
+            assert e[0] == 0 and e[-1] == h and len(e) == world + 1
+            assert all(a <= b for a, b in zip(e, e[1:]))
+            assert all(x % 16 == 0 for x in e[:-1])
+
+
+@pytest.mark.timeout(300)
+def test_two_gloo_ranks_reproduce_the_single_process_result(tmp_path):
+    out = str(tmp_path / "rank0.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    z = np.load(out)
+    scene = _scene()
+    want = np.stack([_render_view(scene, i) for i in range(N_VIEWS)])
+    assert np.array_equal(z["views"], want), "view-sharded orbit differs from the single-process orbit"
+    assert np.array_equal(z["frame"], want[1]), "bands do not concatenate to the full frame"
+    assert float(z["slowest"]) == 2.0  # max over ranks, the timing rule of bench.py
+    assert list(z["edges"]) == vdist.band_edges(H, 2)
