@@ -327,12 +327,15 @@ static void project_one(const vko_camera* cam, const vko_frame* f, const float* 
   if (variant == 1) {
     float theta = atan2f(sin2t, cos2t) / 2.f;
     ct = cosf(theta); st = sinf(theta);
-  } else if (cos2t >= 0.f) { /* theta in [-pi/4, pi/4] */
-    ct = sqrtf(0.5f * (1.f + cos2t));
-    st = (0.5f * sin2t) / ct;
-  } else { /* |theta| in (pi/4, pi/2]; also the NaN lane (D == 0) */
-    st = copysignf(sqrtf(0.5f * (1.f - cos2t)), sin2t);
-    ct = (0.5f * sin2t) / st;
+  } else {
+    /* half-angle identities: h = cos or |sin| of the half angle, whichever is >= 1/sqrt(2) (theta in [-pi/4, pi/4] when
+     * cos 2t >= 0, |theta| in (pi/4, pi/2] otherwise); the other one is (sin 2t / 2) * (1/h) - one IEEE reciprocal, as
+     * for every other quotient of this function.  The NaN lane (D == 0) stays NaN. */
+    float h = sqrtf(0.5f * (1.f + fabsf(cos2t)));
+    float ih = 1.f / h;
+    float q = (0.5f * sin2t) * ih;
+    if (cos2t >= 0.f) { ct = h; st = q; }
+    else { ct = fabsf(q); st = copysignf(h, sin2t); }
   }
 
   /* pos = projection * pos; pos /= pos.w   :136-137 */

@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvkgsb.so")
+# VKGSB_LIB selects another build of the same library (A/B kernel experiments, tools/build_variant.sh); still no fallback
+LIB_PATH = os.environ.get("VKGSB_LIB") or os.path.join(_HERE, "lib", "libvkgsb.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_CAPACITY, ERR_NO_SCENE, ERR_CANCELLED = range(7)
 BLEND_FP32, BLEND_UNORM8 = 0, 1

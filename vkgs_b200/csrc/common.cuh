@@ -102,23 +102,27 @@ __device__ __forceinline__ unsigned long long scan_peek(const unsigned long long
 __device__ __forceinline__ void scan_post(unsigned long long* desc, uint32_t ticket, uint32_t total) {
   if ((threadIdx.x & 31u) == 0) scan_publish(desc + ticket, ticket == 0 ? kScanInclusive : kScanAggregate, total);
 }
-__device__ __forceinline__ uint32_t scan_resolve(unsigned long long* desc, uint32_t ticket, uint32_t total) {
+// scan_resolve can be split so that the first round trip to the descriptors overlaps other work:
+//   w0 = scan_peek_first(desc, ticket); ...independent work...; prefix = scan_resolve_from(desc, ticket, total, w0);
+__device__ __forceinline__ unsigned long long scan_peek_first(const unsigned long long* desc, uint32_t ticket) {
+  const int64_t idx = static_cast<int64_t>(ticket) - 1 - (threadIdx.x & 31u);
+  // lanes before descriptor 0 act as a zero inclusive terminator
+  return idx >= 0 ? scan_peek(desc + idx) : (static_cast<unsigned long long>(kScanInclusive) << 32);
+}
+__device__ __forceinline__ uint32_t scan_resolve_from(unsigned long long* desc, uint32_t ticket, uint32_t total,
+                                                      unsigned long long w) {
   const uint32_t lane = threadIdx.x & 31u;
   if (ticket == 0) return 0u;
   uint32_t prefix = 0;
   int64_t hi = static_cast<int64_t>(ticket) - 1;  // newest descriptor not yet consumed
   while (true) {
-    int64_t idx = hi - lane;
-    unsigned long long w = 0;
-    uint32_t st = kScanInclusive;  // lanes before descriptor 0 act as a zero inclusive terminator
-    uint32_t val = 0;
-    if (idx >= 0) {
-      do {
-        w = scan_peek(desc + idx);
-        st = static_cast<uint32_t>(w >> 32);
-      } while (st == 0u);
-      val = static_cast<uint32_t>(w);
+    const int64_t idx = hi - lane;
+    uint32_t st = static_cast<uint32_t>(w >> 32);
+    while (st == 0u) {  // not posted yet (idx >= 0 here: the terminator lanes carry kScanInclusive)
+      w = scan_peek(desc + idx);
+      st = static_cast<uint32_t>(w >> 32);
     }
+    const uint32_t val = static_cast<uint32_t>(w);
     // first lane (nearest predecessor side) holding an inclusive value terminates the walk
     uint32_t incl_mask = __ballot_sync(0xffffffffu, st == kScanInclusive);
     uint32_t first = __ffs(incl_mask) - 1;
@@ -129,9 +133,14 @@ __device__ __forceinline__ uint32_t scan_resolve(unsigned long long* desc, uint3
     prefix += contrib;
     if (incl_mask != 0u) break;
     hi -= 32;
+    w = hi - lane >= 0 ? scan_peek(desc + (hi - lane)) : (static_cast<unsigned long long>(kScanInclusive) << 32);
   }
   if (lane == 0) scan_publish(desc + ticket, kScanInclusive, prefix + total);
   return prefix;
+}
+__device__ __forceinline__ uint32_t scan_resolve(unsigned long long* desc, uint32_t ticket, uint32_t total) {
+  if (ticket == 0) return 0u;
+  return scan_resolve_from(desc, ticket, total, scan_peek_first(desc, ticket));
 }
 // Both steps back to back.
 __device__ __forceinline__ uint32_t scan_lookback_warp(unsigned long long* desc, uint32_t ticket, uint32_t block_total) {
