@@ -35,7 +35,7 @@ N_VIEWS = 64                      # orbit the steps cycle through
 ORBIT = dict(r=1.5, phi_deg=70.0)  # ~2 M visible of 6.1 M: the reference's "view 2" regime (DETAILS.md:72)
 E2E_BATCH = 8                     # views per vkgsb_draw_batch call in the end-to-end leg
 PARAM_BYTES = 468                 # sizeof(FrameParams): the per-frame host->device upload (a kernel argument)
-KERNELS_PER_FRAME = 10            # set_params, project, 4 depth onesweep passes, bin count / scan / place, blend
+KERNELS_PER_FRAME = 9             # set_params, project, 3 depth onesweep passes, bin count / scan / place, blend
 
 
 def view_camera(i):

@@ -36,21 +36,23 @@ void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl
 struct SortArgs {
   const uint32_t* d_count;  // element count (device)
   uint32_t max_n;           // capacity the launch is sized for
-  uint32_t* keys;           // in/out (result lands here: the pass count is even)
+  uint32_t* keys;           // in; the result lands here when the pass count is even, in keys_alt / vals_alt when odd
   uint32_t* vals;
   uint32_t* keys_alt;       // ping-pong scratch, max_n each
   uint32_t* vals_alt;
-  uint32_t* hist;           // [npass][256]; zero on entry, or already filled when have_hist
+  uint32_t* hist;           // the passes' digit histograms back to back (256 or 512 bins each, <= 1024 in all);
+                            // zero on entry, or already filled when have_hist
   uint32_t* tickets;        // [npass], zero on entry
-  uint32_t* lookback;       // [npass][sort_max_parts(max_n)][256]; cleared by the histogram kernel, or by the
-                            // caller when have_hist
+  uint32_t* lookback;       // sort_lookback_bytes(max_n); cleared by the histogram kernel, or by the caller when
+                            // have_hist
   bool have_hist;           // the producer of the keys already built the digit histograms: no histogram pass
-  int begin_bit;            // first pass digit starts here; passes are 8 bits wide
-  int npass;                // 1, 2 or 4; odd: the result is in keys_alt / vals_alt
+  int begin_bit;            // first pass digit starts here
+  int npass;                // 1 .. 4
+  uint8_t bits[4];          // digit width per pass: 8 (0 reads as 8: the reference's digit) or 9; sum of 2^bits <= 1024
   bool values_only;         // the caller only reads the sorted values: the last pass does not store keys
 };
 uint32_t sort_max_parts(uint32_t max_n);
-size_t sort_lookback_bytes(uint32_t max_n, int npass);
+size_t sort_lookback_bytes(uint32_t max_n);
 void launch_sort(const SortArgs& a, cudaStream_t stream);
 
 // ---- bin.cu: the sorted list split into one nearest-first list of splat slots per coarse bin ------------------------

@@ -289,17 +289,22 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.payload, n};
   CU_TRY(cudaMemsetAsync(r->zero_region, 0, r->zero_bytes, s));
   // look-back words of the depth sort: only partitions of the <= n visible splats can be touched
-  CU_TRY(cudaMemsetAsync(r->lookback_depth, 0, sort_lookback_bytes(n, 4), s));
+  CU_TRY(cudaMemsetAsync(r->lookback_depth, 0, sort_lookback_bytes(n), s));
   if (timed) CU_TRY(cudaEventRecord(r->ev[0], s));
-  launch_project(sc, r->d_fp, r->ctrl, r->desc_project, r->keys, r->slots, r->vis_id, r->rrec, r->bin_rect, r->inst, s);
+  // the depth sort runs an odd number of passes: its input goes to the ping-pong side, its result lands in keys / slots
+  launch_project(sc, r->d_fp, r->ctrl, r->desc_project, r->keys_alt, r->slots_alt, r->vis_id, r->rrec, r->bin_rect, r->inst, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
   SortArgs depth{};
   depth.d_count = &r->ctrl->visible_count;
   depth.max_n = n;
-  depth.keys = r->keys; depth.vals = r->slots; depth.keys_alt = r->keys_alt; depth.vals_alt = r->slots_alt;
+  depth.keys = r->keys_alt; depth.vals = r->slots_alt; depth.keys_alt = r->keys; depth.vals_alt = r->slots;
   depth.hist = r->ctrl->hist_depth; depth.tickets = r->ctrl->sort_ticket; depth.lookback = r->lookback_depth;
-  depth.begin_bit = 0; depth.npass = 4;
-  depth.have_hist = true;  // k_project accumulated the four digit histograms
+  // k_project emits the depth key as the integer (1 - z) * 2^24 in [0, 2^24] (the float 1 - z is always a multiple of
+  // 2^-24, so this is exact and ordered like the reference's float bits): 25 live bits = 3 passes of 8 + 8 + 9 bits
+  // instead of the reference's 4 x 8 over the full word
+  depth.begin_bit = 0; depth.npass = 3;
+  depth.bits[0] = 8; depth.bits[1] = 8; depth.bits[2] = 9;
+  depth.have_hist = true;  // k_project accumulated the three digit histograms
   launch_sort(depth, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[2], s));
   launch_bin(r->d_fp, r->h_fp.ncbins, r->ctrl, r->slots, r->bin_rect, n, r->max_pairs, r->bin, r->ranges, r->bin_slots, s);
@@ -421,7 +426,7 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   ALLOC(r->bin.tile_item, (static_cast<size_t>(r->bin.tile_stride) + 1) * 4);
   ALLOC(r->bin.tile_bin, static_cast<size_t>(kMaxCoarseBins) * r->bin.tile_stride * 4);
   ALLOC(r->bin.bin_total, kMaxCoarseBins * 4);
-  ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats, 4));
+  ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats));
   const size_t nb_proj = project_num_tiles(r->max_splats);
   const size_t ctrl_bytes = (sizeof(Control) + 255) & ~size_t(255);
   r->zero_bytes = ctrl_bytes + nb_proj * 8 + kMaxCoarseBins * sizeof(uint2);
@@ -685,7 +690,15 @@ int vkgsb_read_sorted(vkgsb_renderer* r, uint32_t* keys, uint32_t* ids, uint32_t
   *count = v;
   if (v > capacity) return fail(VKGSB_ERR_CAPACITY, "capacity smaller than the visible count");
   if (v == 0) return VKGSB_OK;
-  if (keys) CU_TRY(cudaMemcpy(keys, r->keys, v * 4ull, cudaMemcpyDeviceToHost));
+  if (keys) {
+    CU_TRY(cudaMemcpy(keys, r->keys, v * 4ull, cudaMemcpyDeviceToHost));
+    // the frame sorts the integer (1 - z) * 2^24; the tap returns the reference's key, floatBitsToUint(1 - z)
+    // (rank.comp:40) - the conversion is exact both ways
+    for (uint32_t i = 0; i < v; ++i) {
+      const float f = static_cast<float>(keys[i]) * 5.9604644775390625e-08f;
+      std::memcpy(&keys[i], &f, 4);
+    }
+  }
   if (ids) {
     // slots_alt is free between frames: gather ids there
     launch_gather_sorted(r->ctrl, r->slots, r->vis_id, r->inst, v, r->slots_alt, nullptr, r->stream);
@@ -750,7 +763,7 @@ int vkgsb_read_scene(vkgsb_renderer* r, float* pos, float* cov, float* opacity, 
 static size_t sort_storage_layout(uint32_t max_n, size_t* off_lookback, size_t* off_keys, size_t* off_vals) {
   size_t o = 4 * 256 * 4 + 64;
   *off_lookback = o;
-  o += sort_lookback_bytes(max_n, 4);
+  o += sort_lookback_bytes(max_n);
   o = (o + 255) & ~size_t(255);
   *off_keys = o;
   o += (static_cast<size_t>(max_n) * 4 + 255) & ~size_t(255);

@@ -11,31 +11,48 @@
 
 namespace vkgsb {
 
-constexpr int kSortThreads = 256;  // == radix: thread d owns digit d in the scan / look-back steps
+constexpr int kSortThreads = 256;  // thread t owns the digits [t * DPT, (t + 1) * DPT) in the scan / look-back steps
 constexpr int kSortItems = 16;
 constexpr int kSortPart = kSortThreads * kSortItems;  // 4096 pairs per partition (PARTITION_SIZE, constants.slang:5)
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kLookBatch = 8;
+constexpr int kMaxBins = 1024;  // digit bins of all passes together: 4 x 256 (the reference's layout) or 256 + 256 + 512
 constexpr uint32_t kFlagAggregate = 1u << 30, kFlagInclusive = 2u << 30, kFlagMask = 3u << 30, kValueMask = ~kFlagMask;
 
 __host__ __device__ inline uint32_t parts_of(uint32_t n) { return (n + kSortPart - 1) / kSortPart; }
 uint32_t sort_max_parts(uint32_t max_n) { return parts_of(max_n); }
-size_t sort_lookback_bytes(uint32_t max_n, int npass) {
-  return static_cast<size_t>(npass) * sort_max_parts(max_n) * 256 * sizeof(uint32_t);
+size_t sort_lookback_bytes(uint32_t max_n) { return static_cast<size_t>(sort_max_parts(max_n)) * kMaxBins * sizeof(uint32_t); }
+
+__host__ __device__ inline int pass_bits(const SortArgs& a, int p) { return a.bits[p] ? a.bits[p] : 8; }
+// first bit and first histogram bin of pass p
+__host__ __device__ inline void pass_layout(const SortArgs& a, int p, int* shift, uint32_t* bin0) {
+  int sh = a.begin_bit;
+  uint32_t b = 0;
+  for (int q = 0; q < p; ++q) {
+    sh += pass_bits(a, q);
+    b += 1u << pass_bits(a, q);
+  }
+  *shift = sh;
+  *bin0 = b;
 }
 
 // All digit histograms in one pass over the keys; also clears the look-back words the scatter passes will use.
 __global__ void __launch_bounds__(256) k_sort_hist(SortArgs a) {
-  __shared__ uint32_t s_hist[4 * 256];
+  __shared__ uint32_t s_hist[kMaxBins];
   const uint32_t n = min(*a.d_count, a.max_n);
   const uint32_t tid = threadIdx.x;
-  for (int i = tid; i < a.npass * 256; i += 256) s_hist[i] = 0;
+  for (int i = tid; i < kMaxBins; i += 256) s_hist[i] = 0;
   __syncthreads();
 
+  // look-back words: pass p owns [bin0(p) * max_parts, ...) as [partition][digit]; only the first nparts rows are used
   const uint32_t nparts = (n + kSortPart - 1) / kSortPart, max_parts = parts_of(a.max_n);
   for (int p = 0; p < a.npass; ++p) {
-    uint32_t* lb = a.lookback + static_cast<size_t>(p) * max_parts * 256;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + tid; i < static_cast<size_t>(nparts) * 256;
+    int sh;
+    uint32_t b0;
+    pass_layout(a, p, &sh, &b0);
+    const uint32_t bins = 1u << pass_bits(a, p);
+    uint32_t* lb = a.lookback + static_cast<size_t>(b0) * max_parts;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + tid; i < static_cast<size_t>(nparts) * bins;
          i += static_cast<size_t>(gridDim.x) * 256)
       lb[i] = 0u;
   }
@@ -54,19 +71,32 @@ __global__ void __launch_bounds__(256) k_sort_hist(SortArgs a) {
     const uint32_t active = __ballot_sync(0xffffffffu, ok);
     if (!ok) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
+      int sh = a.begin_bit;
+      uint32_t b0 = 0;
       for (int p = 0; p < a.npass; ++p) {
-        const uint32_t d = (ks[j] >> (a.begin_bit + 8 * p)) & 255u;
+        const int bits = pass_bits(a, p);
+        const uint32_t d = (ks[j] >> sh) & ((1u << bits) - 1u);
         const uint32_t peers = __match_any_sync(active, d);
-        if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * 256 + d], __popc(peers));
+        if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[b0 + d], __popc(peers));
+        sh += bits;
+        b0 += 1u << bits;
       }
+    }
   }
   if (blockIdx.x == 0 && tid < (n & 3u)) {
     uint32_t k = a.keys[n4 * 4 + tid];
-    for (int p = 0; p < a.npass; ++p) atomicAdd(&s_hist[p * 256 + ((k >> (a.begin_bit + 8 * p)) & 255u)], 1u);
+    int sh = a.begin_bit;
+    uint32_t b0 = 0;
+    for (int p = 0; p < a.npass; ++p) {
+      const int bits = pass_bits(a, p);
+      atomicAdd(&s_hist[b0 + ((k >> sh) & ((1u << bits) - 1u))], 1u);
+      sh += bits;
+      b0 += 1u << bits;
+    }
   }
   __syncthreads();
-  for (int i = tid; i < a.npass * 256; i += 256) {
+  for (int i = tid; i < kMaxBins; i += 256) {
     uint32_t c = s_hist[i];
     if (c) atomicAdd(&a.hist[i], c);
   }
@@ -81,49 +111,68 @@ __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// One digit pass: rank within the partition (warp match + per-warp histograms), chained scan across partitions,
-// shared-memory reorder, coalesced scatter.  Stable: order inside a partition is (warp, item, lane) == input order.
-__global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int pass) {
-  __shared__ uint32_t s_whist[kSortWarps * 256];
+// One digit pass of BITS bits: rank within the partition (warp match + per-warp histograms), chained scan across
+// partitions, shared-memory reorder, coalesced scatter.  Stable: order inside a partition is (warp, item, lane) == input
+// order.  BITS = 8 is the reference's digit; BITS = 9 lets the 25-bit depth keys of the frame path finish in 3 passes.
+template <int BITS>
+__global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int pass, int shift, uint32_t bin0) {
+  constexpr int BINS = 1 << BITS, DPT = BINS / kSortThreads;
+  constexpr uint32_t MASK = BINS - 1;
+  static_assert(DPT >= 1 && kSortWarps * BINS <= kSortPart, "the value stage reuses the per-warp histograms' storage");
   __shared__ uint32_t s_keys[kSortPart];
-  __shared__ uint32_t s_vals[kSortPart];
-  __shared__ uint32_t s_gbase[256];  // global index of local sorted position 0 of digit d, minus its local base
-  __shared__ uint32_t s_lbase[256];
+  __shared__ uint32_t s_vals[kSortPart];  // also the per-warp digit counters [kSortWarps][BINS] until the values land
+  __shared__ uint32_t s_gbase[BINS];      // global index of local sorted position 0 of digit d, minus its local base
+  __shared__ uint32_t s_lbase[BINS];
   __shared__ uint32_t s_scan[kSortWarps];
   __shared__ uint32_t s_part;
+  uint32_t* s_whist = s_vals;
 
   const uint32_t n = min(*a.d_count, a.max_n);
   const uint32_t nparts = (n + kSortPart - 1) / kSortPart, max_parts = parts_of(a.max_n);
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const int shift = a.begin_bit + 8 * pass;
   const uint32_t* __restrict__ src_k = (pass & 1) ? a.keys_alt : a.keys;
   const uint32_t* __restrict__ src_v = (pass & 1) ? a.vals_alt : a.vals;
   uint32_t* __restrict__ dst_k = (pass & 1) ? a.keys : a.keys_alt;
   uint32_t* __restrict__ dst_v = (pass & 1) ? a.vals : a.vals_alt;
-  uint32_t* __restrict__ lookback = a.lookback + static_cast<size_t>(pass) * max_parts * 256;
+  uint32_t* __restrict__ lookback = a.lookback + static_cast<size_t>(bin0) * max_parts;
   const bool store_keys = !(a.values_only && pass == a.npass - 1);
 
-  // exclusive scan of this pass's global histogram (every block recomputes it: 256 words)
-  uint32_t gexcl;
-  {
-    uint32_t c = a.hist[pass * 256 + tid], v = c;
+  // block-wide exclusive scan of one value per thread
+  auto block_excl = [&](uint32_t v) {
+    uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= static_cast<uint32_t>(o)) v += t;
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= static_cast<uint32_t>(o)) incl += t;
     }
-    if (lane == 31) s_scan[warp] = v;
+    if (lane == 31) s_scan[warp] = incl;
     __syncthreads();
     uint32_t wbase = 0;
     for (uint32_t w = 0; w < warp; ++w) wbase += s_scan[w];
-    gexcl = wbase + v - c;
     __syncthreads();
+    return wbase + incl - v;
+  };
+
+  // exclusive scan of this pass's global histogram (every block recomputes it: BINS words)
+  uint32_t gexcl[DPT];
+  {
+    uint32_t c[DPT], sum = 0;
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+      c[j] = a.hist[bin0 + tid * DPT + j];
+      sum += c[j];
+    }
+    uint32_t run = block_excl(sum);
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+      gexcl[j] = run;
+      run += c[j];
+    }
   }
 
   while (true) {
     if (tid == 0) s_part = atomicAdd(&a.tickets[pass], 1u);
-#pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) s_whist[w * 256 + tid] = 0u;
+    for (int i = tid; i < kSortWarps * BINS; i += kSortThreads) s_whist[i] = 0u;
     __syncthreads();
     const uint32_t part = s_part;
     if (part >= nparts) return;
@@ -138,10 +187,10 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int 
       const uint32_t li = wbase + i * 32 + lane;
       key[i] = (li < valid) ? __ldg(src_k + pbase + li) : 0xffffffffu;  // padding ranks after every real key
     }
-    uint32_t* wh = s_whist + warp * 256;
+    uint32_t* wh = s_whist + warp * BINS;
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
-      const uint32_t d = (key[i] >> shift) & 255u;
+      const uint32_t d = (key[i] >> shift) & MASK;
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
       const uint32_t leader = __ffs(peers) - 1;
       uint32_t prev = 0;
@@ -155,70 +204,94 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int 
     }
     __syncthreads();
 
-    // ---- thread d: digit d across warps -> per-warp exclusive bases, block total
-    uint32_t total = 0;
+    // ---- this thread's digits across warps -> per-warp exclusive bases, block totals
+    uint32_t total[DPT];
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-      uint32_t c = s_whist[w * 256 + tid];
-      s_whist[w * 256 + tid] = total;
-      total += c;
+    for (int j = 0; j < DPT; ++j) {
+      const uint32_t d = tid * DPT + j;
+      uint32_t t = 0;
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        uint32_t c = s_whist[w * BINS + d];
+        s_whist[w * BINS + d] = t;
+        t += c;
+      }
+      total[j] = t;
     }
     // ---- chained scan over partitions (decoupled look-back), one word per (partition, digit)
-    uint32_t excl = 0;
+    uint32_t excl[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) excl[j] = 0;
     {
-      uint32_t* mine = lookback + static_cast<size_t>(part) * 256 + tid;
+      uint32_t* mine = lookback + static_cast<size_t>(part) * BINS + tid * DPT;
       if (part == 0) {
-        st_relaxed(mine, kFlagInclusive | total);
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) st_relaxed(mine + j, kFlagInclusive | total[j]);
       } else {
-        st_relaxed(mine, kFlagAggregate | total);
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) st_relaxed(mine + j, kFlagAggregate | total[j]);
         // Walk back kLookBatch predecessors per round trip: when the whole input is one wave of partitions (a 2 M-key
         // depth sort is 500 of them) every aggregate appears at about the same time and a one-at-a-time walk would
         // serialise hundreds of L2 latencies.
-        int64_t q = static_cast<int64_t>(part) - 1;
-        bool fin = false;
-        while (!fin) {
-          uint32_t w[kLookBatch];
+        int64_t q[DPT];
+        bool fin[DPT];
 #pragma unroll
-          for (int j = 0; j < kLookBatch; ++j)
-            w[j] = (q - j >= 0) ? ld_relaxed(lookback + static_cast<size_t>(q - j) * 256 + tid) : kFlagInclusive;
-          int used = 0;
-#pragma unroll
-          for (int j = 0; j < kLookBatch; ++j) {
-            const uint32_t f = w[j] & kFlagMask;
-            if (!fin && used == j && f != 0u) {
-              excl += w[j] & kValueMask;
-              used = j + 1;
-              fin = f == kFlagInclusive;
-            }
-          }
-          q -= used;
+        for (int j = 0; j < DPT; ++j) {
+          q[j] = static_cast<int64_t>(part) - 1;
+          fin[j] = false;
         }
-        st_relaxed(mine, kFlagInclusive | (excl + total));
+        bool all_fin = false;
+        while (!all_fin) {
+          uint32_t w[DPT][kLookBatch];
+#pragma unroll
+          for (int j = 0; j < DPT; ++j)
+#pragma unroll
+            for (int b = 0; b < kLookBatch; ++b)
+              w[j][b] = (!fin[j] && q[j] - b >= 0)
+                            ? ld_relaxed(lookback + static_cast<size_t>(q[j] - b) * BINS + tid * DPT + j)
+                            : kFlagInclusive;
+          all_fin = true;
+#pragma unroll
+          for (int j = 0; j < DPT; ++j) {
+            int used = 0;
+            bool f = fin[j];
+#pragma unroll
+            for (int b = 0; b < kLookBatch; ++b) {
+              const uint32_t fl = w[j][b] & kFlagMask;
+              if (!f && used == b && fl != 0u) {
+                excl[j] += w[j][b] & kValueMask;
+                used = b + 1;
+                f = fl == kFlagInclusive;
+              }
+            }
+            q[j] -= used;
+            fin[j] = f;
+            all_fin = all_fin && f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) st_relaxed(mine + j, kFlagInclusive | (excl[j] + total[j]));
       }
     }
     // ---- block-local exclusive scan of totals over digits
-    uint32_t lexcl;
     {
-      uint32_t v = total;
+      uint32_t sum = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= static_cast<uint32_t>(o)) v += t;
+      for (int j = 0; j < DPT; ++j) sum += total[j];
+      uint32_t run = block_excl(sum);
+#pragma unroll
+      for (int j = 0; j < DPT; ++j) {
+        s_lbase[tid * DPT + j] = run;
+        s_gbase[tid * DPT + j] = gexcl[j] + excl[j] - run;
+        run += total[j];
       }
-      if (lane == 31) s_scan[warp] = v;
-      __syncthreads();
-      uint32_t wb = 0;
-      for (uint32_t w = 0; w < warp; ++w) wb += s_scan[w];
-      lexcl = wb + v - total;
     }
-    s_lbase[tid] = lexcl;
-    s_gbase[tid] = gexcl + excl - lexcl;
     __syncthreads();
 
     // ---- reorder through shared memory
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
-      const uint32_t d = (key[i] >> shift) & 255u;
+      const uint32_t d = (key[i] >> shift) & MASK;
       pos[i] += s_lbase[d] + wh[d];
       s_keys[pos[i]] = key[i];
     }
@@ -229,13 +302,13 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int 
       const uint32_t li = wbase + i * 32 + lane;
       val[i] = (li < valid) ? __ldg(src_v + pbase + li) : 0u;
     }
-    __syncthreads();
+    __syncthreads();  // every wh[] has been read: its storage now takes the values
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
       const uint32_t j = i * kSortThreads + tid;
       if (j < valid) {
         const uint32_t k = s_keys[j];
-        if (store_keys) dst_k[s_gbase[(k >> shift) & 255u] + j] = k;
+        if (store_keys) dst_k[s_gbase[(k >> shift) & MASK] + j] = k;
       }
     }
 #pragma unroll
@@ -244,7 +317,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int 
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
       const uint32_t j = i * kSortThreads + tid;
-      if (j < valid) dst_v[s_gbase[(s_keys[j] >> shift) & 255u] + j] = s_vals[j];
+      if (j < valid) dst_v[s_gbase[(s_keys[j] >> shift) & MASK] + j] = s_vals[j];
     }
     __syncthreads();  // s_part / s_whist / s_keys are rewritten by the next iteration
   }
@@ -256,7 +329,15 @@ void launch_sort(const SortArgs& a, cudaStream_t stream) {
   int hist_blocks = static_cast<int>(min(static_cast<uint32_t>(148 * 8), (a.max_n + 4095u) / 4096u));
   if (!a.have_hist) k_sort_hist<<<hist_blocks, 256, 0, stream>>>(a);
   int blocks = static_cast<int>(min(parts, static_cast<uint32_t>(148 * 4)));
-  for (int p = 0; p < a.npass; ++p) k_sort_onesweep<<<blocks, kSortThreads, 0, stream>>>(a, p);
+  for (int p = 0; p < a.npass; ++p) {
+    int shift;
+    uint32_t bin0;
+    pass_layout(a, p, &shift, &bin0);
+    if (pass_bits(a, p) == 9)
+      k_sort_onesweep<9><<<blocks, kSortThreads, 0, stream>>>(a, p, shift, bin0);
+    else
+      k_sort_onesweep<8><<<blocks, kSortThreads, 0, stream>>>(a, p, shift, bin0);
+  }
 }
 
 }  // namespace vkgsb
