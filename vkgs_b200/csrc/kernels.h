@@ -50,6 +50,8 @@ struct SortArgs {
   int npass;                // 1 .. 4
   uint8_t bits[4];          // digit width per pass: 8 (0 reads as 8: the reference's digit) or 9; sum of 2^bits <= 1024
   bool values_only;         // the caller only reads the sorted values: the last pass does not store keys
+  uint32_t clustered_passes;  // bit p: pass p's digit takes only a handful of values (ranked with match.any, one round
+                              // per distinct value, instead of one ballot per bit)
 };
 uint32_t sort_max_parts(uint32_t max_n);
 size_t sort_lookback_bytes(uint32_t max_n);

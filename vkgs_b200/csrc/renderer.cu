@@ -304,6 +304,7 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   // instead of the reference's 4 x 8 over the full word
   depth.begin_bit = 0; depth.npass = 3;
   depth.bits[0] = 8; depth.bits[1] = 8; depth.bits[2] = 9;
+  depth.clustered_passes = 1u << 2;  // bits 16..24 of (1 - z) * 2^24: a few values per warp
   depth.have_hist = true;  // k_project accumulated the three digit histograms
   launch_sort(depth, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[2], s));

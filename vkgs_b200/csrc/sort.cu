@@ -114,7 +114,7 @@ __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
 // One digit pass of BITS bits: rank within the partition (warp match + per-warp histograms), chained scan across
 // partitions, shared-memory reorder, coalesced scatter.  Stable: order inside a partition is (warp, item, lane) == input
 // order.  BITS = 8 is the reference's digit; BITS = 9 lets the 25-bit depth keys of the frame path finish in 3 passes.
-template <int BITS>
+template <int BITS, bool MATCH>
 __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int pass, int shift, uint32_t bin0) {
   constexpr int BINS = 1 << BITS, DPT = BINS / kSortThreads;
   constexpr uint32_t MASK = BINS - 1;
@@ -188,10 +188,29 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int 
       key[i] = (li < valid) ? __ldg(src_k + pbase + li) : 0xffffffffu;  // padding ranks after every real key
     }
     uint32_t* wh = s_whist + warp * BINS;
+    // lanes holding the same digit, from BITS ballots (match.any costs one round per distinct value in the warp -
+    // ~30 of them for a dense digit: it took a quarter of the kernel's stall samples); all 16 items first, so the
+    // votes pipeline
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
       const uint32_t d = (key[i] >> shift) & MASK;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      uint32_t m = 0xffffffffu;
+      if (MATCH) {  // the caller's hint: this digit takes a handful of values (a depth key's top bits) - few rounds
+        m = __match_any_sync(0xffffffffu, d);
+      } else {
+#pragma unroll
+        for (int b = 0; b < BITS; ++b) {
+          const bool bit = (d >> b) & 1u;
+          const uint32_t v = __ballot_sync(0xffffffffu, bit);
+          m &= bit ? v : ~v;
+        }
+      }
+      pos[i] = m;
+    }
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+      const uint32_t d = (key[i] >> shift) & MASK;
+      const uint32_t peers = pos[i];
       const uint32_t leader = __ffs(peers) - 1;
       uint32_t prev = 0;
       if (lane == leader) {
@@ -333,10 +352,14 @@ void launch_sort(const SortArgs& a, cudaStream_t stream) {
     int shift;
     uint32_t bin0;
     pass_layout(a, p, &shift, &bin0);
-    if (pass_bits(a, p) == 9)
-      k_sort_onesweep<9><<<blocks, kSortThreads, 0, stream>>>(a, p, shift, bin0);
-    else
-      k_sort_onesweep<8><<<blocks, kSortThreads, 0, stream>>>(a, p, shift, bin0);
+    const bool clustered = (a.clustered_passes >> p) & 1u;
+    if (pass_bits(a, p) == 9) {
+      if (clustered) k_sort_onesweep<9, true><<<blocks, kSortThreads, 0, stream>>>(a, p, shift, bin0);
+      else k_sort_onesweep<9, false><<<blocks, kSortThreads, 0, stream>>>(a, p, shift, bin0);
+    } else {
+      if (clustered) k_sort_onesweep<8, true><<<blocks, kSortThreads, 0, stream>>>(a, p, shift, bin0);
+      else k_sort_onesweep<8, false><<<blocks, kSortThreads, 0, stream>>>(a, p, shift, bin0);
+    }
   }
 }
 
