@@ -15,13 +15,36 @@ constexpr int kSortThreads = 256;  // thread t owns the digits [t * DPT, (t + 1)
 constexpr int kSortItems = 16;
 constexpr int kSortPart = kSortThreads * kSortItems;  // 4096 pairs per partition (PARTITION_SIZE, constants.slang:5)
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kLookBatch = 8;
 constexpr int kMaxBins = 1024;  // digit bins of all passes together: 4 x 256 (the reference's layout) or 256 + 256 + 512
-constexpr uint32_t kFlagAggregate = 1u << 30, kFlagInclusive = 2u << 30, kFlagMask = 3u << 30, kValueMask = ~kFlagMask;
+constexpr uint32_t kFlagAggregate = 1u << 30, kFlagMask = 3u << 30, kValueMask = ~kFlagMask;
 
 __host__ __device__ inline uint32_t parts_of(uint32_t n) { return (n + kSortPart - 1) / kSortPart; }
 uint32_t sort_max_parts(uint32_t max_n) { return parts_of(max_n); }
-size_t sort_lookback_bytes(uint32_t max_n) { return static_cast<size_t>(sort_max_parts(max_n)) * kMaxBins * sizeof(uint32_t); }
+
+// The partitions' digit counts form an 8-ary tree (k_sort_onesweep): level 0 = one row per partition, level k = one row
+// per aligned group of 8 rows of level k-1, up to a single row.  off[k] = first row of level k.
+struct SortLevels {
+  uint32_t off[8];
+  int K;
+  uint32_t total;
+};
+__host__ __device__ inline SortLevels sort_levels(uint32_t nparts) {
+  SortLevels lv;
+  lv.K = 0;
+  uint32_t rows = nparts ? nparts : 1u, o = 0;
+  while (true) {
+    lv.off[lv.K++] = o;
+    o += rows;
+    if (rows <= 1u || lv.K == 8) break;
+    rows = (rows + 7u) / 8u;
+  }
+  lv.total = o;
+  return lv;
+}
+// rows x (all passes' bins) words + per pass one arrival counter per row
+size_t sort_lookback_bytes(uint32_t max_n) {
+  return static_cast<size_t>(sort_levels(sort_max_parts(max_n)).total) * (kMaxBins + 4) * sizeof(uint32_t);
+}
 
 __host__ __device__ inline int pass_bits(const SortArgs& a, int p) { return a.bits[p] ? a.bits[p] : 8; }
 // first bit and first histogram bin of pass p
@@ -44,18 +67,11 @@ __global__ void __launch_bounds__(256) k_sort_hist(SortArgs a) {
   for (int i = tid; i < kMaxBins; i += 256) s_hist[i] = 0;
   __syncthreads();
 
-  // look-back words: pass p owns [bin0(p) * max_parts, ...) as [partition][digit]; only the first nparts rows are used
-  const uint32_t nparts = (n + kSortPart - 1) / kSortPart, max_parts = parts_of(a.max_n);
-  for (int p = 0; p < a.npass; ++p) {
-    int sh;
-    uint32_t b0;
-    pass_layout(a, p, &sh, &b0);
-    const uint32_t bins = 1u << pass_bits(a, p);
-    uint32_t* lb = a.lookback + static_cast<size_t>(b0) * max_parts;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + tid; i < static_cast<size_t>(nparts) * bins;
-         i += static_cast<size_t>(gridDim.x) * 256)
-      lb[i] = 0u;
-  }
+  // the tree of partition aggregates and its arrival counters: laid out for the actual partition count
+  const uint32_t nparts = (n + kSortPart - 1) / kSortPart;
+  const size_t used = static_cast<size_t>(sort_levels(nparts).total) * (kMaxBins + 4);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + tid; i < used; i += static_cast<size_t>(gridDim.x) * 256)
+    a.lookback[i] = 0u;
 
   // Depth keys and tile ids are heavily clustered in their upper digits (a handful of exponent values; runs of
   // neighbouring tiles), so lanes are aggregated with match.any first: one shared-memory atomic per distinct digit
@@ -115,7 +131,7 @@ __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
 // partitions, shared-memory reorder, coalesced scatter.  Stable: order inside a partition is (warp, item, lane) == input
 // order.  BITS = 8 is the reference's digit; BITS = 9 lets the 25-bit depth keys of the frame path finish in 3 passes.
 template <int BITS, bool MATCH>
-__global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int pass, int shift, uint32_t bin0) {
+__global__ void __launch_bounds__(kSortThreads, 4) k_sort_onesweep(SortArgs a, int pass, int shift, uint32_t bin0) {
   constexpr int BINS = 1 << BITS, DPT = BINS / kSortThreads;
   constexpr uint32_t MASK = BINS - 1;
   static_assert(DPT >= 1 && kSortWarps * BINS <= kSortPart, "the value stage reuses the per-warp histograms' storage");
@@ -124,17 +140,21 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int 
   __shared__ uint32_t s_gbase[BINS];      // global index of local sorted position 0 of digit d, minus its local base
   __shared__ uint32_t s_lbase[BINS];
   __shared__ uint32_t s_scan[kSortWarps];
-  __shared__ uint32_t s_part;
+  __shared__ uint32_t s_part, s_arrive;
   uint32_t* s_whist = s_vals;
 
   const uint32_t n = min(*a.d_count, a.max_n);
-  const uint32_t nparts = (n + kSortPart - 1) / kSortPart, max_parts = parts_of(a.max_n);
+  const uint32_t nparts = (n + kSortPart - 1) / kSortPart;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t* __restrict__ src_k = (pass & 1) ? a.keys_alt : a.keys;
   const uint32_t* __restrict__ src_v = (pass & 1) ? a.vals_alt : a.vals;
   uint32_t* __restrict__ dst_k = (pass & 1) ? a.keys : a.keys_alt;
   uint32_t* __restrict__ dst_v = (pass & 1) ? a.vals : a.vals_alt;
-  uint32_t* __restrict__ lookback = a.lookback + static_cast<size_t>(bin0) * max_parts;
+  // tree of partition aggregates (below): rows of all levels back to back, BINS words each; arrival counters behind
+  // the passes' rows
+  const SortLevels lv = sort_levels(nparts);
+  uint32_t* __restrict__ lookback = a.lookback + static_cast<size_t>(bin0) * lv.total;
+  uint32_t* __restrict__ counters = a.lookback + static_cast<size_t>(kMaxBins) * lv.total + static_cast<size_t>(pass) * lv.total;
   const bool store_keys = !(a.values_only && pass == a.npass - 1);
 
   // block-wide exclusive scan of one value per thread
@@ -237,59 +257,57 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_onesweep(SortArgs a, int 
       }
       total[j] = t;
     }
-    // ---- chained scan over partitions (decoupled look-back), one word per (partition, digit)
+    // ---- exclusive prefix over the partitions before this one, per digit: an 8-ary tree of aggregates.
+    // Level 0 holds one word per (partition, digit); a level-k word is the sum of an aligned group of 8 words of level
+    // k-1, published by whichever CTA arrives LAST in that group (an arrival counter per group).  A prefix is then
+    // <= 7 earlier siblings per level - words that depend on nobody's prefix.  The usual chained look-back serialises
+    // here: a depth sort is ONE wave of ~500 partitions that all post at the same moment, and the first inclusive
+    // value crept forward 8 partitions per L2 round trip (30 us of a 37 us pass; with every partition resident 110 us).
     uint32_t excl[DPT];
 #pragma unroll
     for (int j = 0; j < DPT; ++j) excl[j] = 0;
     {
-      uint32_t* mine = lookback + static_cast<size_t>(part) * BINS + tid * DPT;
-      if (part == 0) {
+      const uint32_t* off = lv.off;
 #pragma unroll
-        for (int j = 0; j < DPT; ++j) st_relaxed(mine + j, kFlagInclusive | total[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < DPT; ++j) st_relaxed(mine + j, kFlagAggregate | total[j]);
-        // Walk back kLookBatch predecessors per round trip: when the whole input is one wave of partitions (a 2 M-key
-        // depth sort is 500 of them) every aggregate appears at about the same time and a one-at-a-time walk would
-        // serialise hundreds of L2 latencies.
-        int64_t q[DPT];
-        bool fin[DPT];
+      for (int j = 0; j < DPT; ++j)
+        st_relaxed(lookback + (static_cast<size_t>(off[0]) + part) * BINS + tid * DPT + j, kFlagAggregate | total[j]);
+      // climb: the last arriver of a complete group sums it and arrives, in turn, at the group's parent
+      uint32_t idx = part;
+      for (int k = 0; k + 1 < lv.K; ++k) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_arrive = atomicAdd(&counters[off[k + 1] + (idx >> 3)], 1u);
+        __syncthreads();
+        if (s_arrive != 7u) break;  // CTA-uniform; a partial group at the end of a level never completes and is never read
+        __threadfence();
 #pragma unroll
         for (int j = 0; j < DPT; ++j) {
-          q[j] = static_cast<int64_t>(part) - 1;
-          fin[j] = false;
+          const uint32_t* row = lookback + (static_cast<size_t>(off[k]) + (idx & ~7u)) * BINS + tid * DPT + j;
+          uint32_t w[8], sum = 0;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) w[m] = ld_relaxed(row + static_cast<size_t>(m) * BINS);
+#pragma unroll
+          for (int m = 0; m < 8; ++m) sum += w[m] & kValueMask;
+          st_relaxed(lookback + (static_cast<size_t>(off[k + 1]) + (idx >> 3)) * BINS + tid * DPT + j, kFlagAggregate | sum);
         }
-        bool all_fin = false;
-        while (!all_fin) {
-          uint32_t w[DPT][kLookBatch];
+        idx >>= 3;
+      }
+      // descend: earlier siblings of this partition's ancestor at every level
+      for (int k = 0; k < lv.K; ++k) {
+        const uint32_t me = part >> (3 * k), nsib = me & 7u;
+        if (nsib == 0u) continue;
 #pragma unroll
-          for (int j = 0; j < DPT; ++j)
+        for (int j = 0; j < DPT; ++j) {
+          const uint32_t* row = lookback + (static_cast<size_t>(off[k]) + (me & ~7u)) * BINS + tid * DPT + j;
+          uint32_t w[7];
 #pragma unroll
-            for (int b = 0; b < kLookBatch; ++b)
-              w[j][b] = (!fin[j] && q[j] - b >= 0)
-                            ? ld_relaxed(lookback + static_cast<size_t>(q[j] - b) * BINS + tid * DPT + j)
-                            : kFlagInclusive;
-          all_fin = true;
+          for (int m = 0; m < 7; ++m) w[m] = static_cast<uint32_t>(m) < nsib ? ld_relaxed(row + static_cast<size_t>(m) * BINS) : kFlagAggregate;
 #pragma unroll
-          for (int j = 0; j < DPT; ++j) {
-            int used = 0;
-            bool f = fin[j];
-#pragma unroll
-            for (int b = 0; b < kLookBatch; ++b) {
-              const uint32_t fl = w[j][b] & kFlagMask;
-              if (!f && used == b && fl != 0u) {
-                excl[j] += w[j][b] & kValueMask;
-                used = b + 1;
-                f = fl == kFlagInclusive;
-              }
-            }
-            q[j] -= used;
-            fin[j] = f;
-            all_fin = all_fin && f;
+          for (int m = 0; m < 7; ++m) {
+            while ((w[m] & kFlagMask) == 0u) w[m] = ld_relaxed(row + static_cast<size_t>(m) * BINS);  // not posted yet
+            excl[j] += w[m] & kValueMask;
           }
         }
-#pragma unroll
-        for (int j = 0; j < DPT; ++j) st_relaxed(mine + j, kFlagInclusive | (excl[j] + total[j]));
       }
     }
     // ---- block-local exclusive scan of totals over digits
