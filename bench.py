@@ -35,6 +35,8 @@ N_VIEWS = 64                      # orbit the steps cycle through
 ORBIT = dict(r=1.5, phi_deg=70.0)  # ~2 M visible of 6.1 M: the reference's "view 2" regime (DETAILS.md:72)
 E2E_BATCH = 8                     # views per vkgsb_draw_batch call in the end-to-end leg
 PARAM_BYTES = 468                 # sizeof(FrameParams): the per-frame host->device upload (a kernel argument)
+WORKLOAD = ("C2 bicycle-shaped 6,131,954 splats SH3, 1600x900, 64-view orbit r=1.5 phi=70deg "
+            "(~2 M visible, the reference's 'view 2' regime)")
 KERNELS_PER_FRAME = 9             # set_params, project, 3 depth onesweep passes, bin count / scan / place, blend
 
 
@@ -99,6 +101,20 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read + dram__bytes_write per k_project launch, from the newest committed `ncu --set full` capture
+    (tools/ncu_traffic.py -> profiles/*_k_project_traffic.json); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_k_project_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        d = json.load(open(files[-1]))
+        return float(d["dram_bytes_per_launch"]), os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 def cpu_sample(rows_fn, threads_note=""):
     """CPU restatement of the reference path (oracle, OpenMP) on a bounded sample: the whole cull / sort / projection
     of one frame, and the rasteriser on a 16-row band scaled to the frame height."""
@@ -154,7 +170,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 bicycle-shaped 6,131,954 splats SH3, 1600x900, orbit r=1.5 (~2 M visible)",
+            "config": {"workload": WORKLOAD, "sample_view": 0,
                        "note": "CPU restatement of the reference's shaders (oracle/, C + OpenMP); the reference's Vulkan "
                                "build / lavapipe is not available on this image"},
             "cpu_baseline": cb,
@@ -282,6 +298,7 @@ def main():
     proj_gbs = alg_bytes / (stage["ms_project"] * 1e-3) / 1e9
     sort_gkeys = V_mean / (stage["ms_sort"] * 1e-3) / 1e9
     dominant = max(("ms_project", "ms_sort", "ms_bin", "ms_blend"), key=lambda k: stage[k])
+    traffic, traffic_src = ncu_traffic()
 
     if rank == 0:
         fps = world * K / (ms * 1e-3)
@@ -289,8 +306,7 @@ def main():
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 bicycle-shaped 6,131,954 splats SH3, 1600x900, 64-view orbit r=1.5 phi=70deg "
-                                   "(~2 M visible, the reference's 'view 2' regime)",
+            "config": {"workload": WORKLOAD,
                        "blend": args.blend, "visible_mean": V_mean, "pairs_mean": D_mean,
                        "parallelism": f"views sharded over {world} GPU(s), scene replicated, images gathered to rank 0 (NCCL)"
                        if world > 1 else "single GPU",
@@ -301,7 +317,8 @@ def main():
             "sort_gkeys_per_s": sort_gkeys,
             "sort_hbm_frac": 68.0 * V_mean / (stage["ms_sort"] * 1e-3) / 1e9 / hbm_peak,
             "roofline": {"kernel": "k_project", "bound": "hbm", "achieved": proj_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": proj_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": proj_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_kind": peak_kind,
                          "algorithmic_bytes": alg_bytes, "share_of_step": stage["ms_project"] / stage["ms_total"],
                          "dominant_by_time": dominant.replace("ms_", "")},
             "e2e": {"value": world * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": PARAM_BYTES, "batch": E2E_BATCH,

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) k_sort_onesweep(SortArgs a, i
   __shared__ uint32_t s_gbase[BINS];      // global index of local sorted position 0 of digit d, minus its local base
   __shared__ uint32_t s_lbase[BINS];
   __shared__ uint32_t s_scan[kSortWarps];
+  __shared__ uint32_t s_cnt[BINS];  // the partition's digit counts, posted before the (much longer) ranking
   __shared__ uint32_t s_part, s_arrive;
   uint32_t* s_whist = s_vals;
 
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) k_sort_onesweep(SortArgs a, i
   while (true) {
     if (tid == 0) s_part = atomicAdd(&a.tickets[pass], 1u);
     for (int i = tid; i < kSortWarps * BINS; i += kSortThreads) s_whist[i] = 0u;
+    for (int i = tid; i < BINS; i += kSortThreads) s_cnt[i] = 0u;
     __syncthreads();
     const uint32_t part = s_part;
     if (part >= nparts) return;
@@ -207,6 +209,52 @@ __global__ void __launch_bounds__(kSortThreads, 4) k_sort_onesweep(SortArgs a, i
       const uint32_t li = wbase + i * 32 + lane;
       key[i] = (li < valid) ? __ldg(src_k + pbase + li) : 0xffffffffu;  // padding ranks after every real key
     }
+    // ---- the partition's digit counts, posted BEFORE the ranking: every partition's prefix needs every earlier
+    // partition's counts, so in a single wave the pass is as slow as the slowest partition's time-to-post.  Counting is
+    // 16 shared-memory atomics per thread; the ranking below (ballots, serial per-warp counters) is ten times that and
+    // now overlaps the tree reduction.
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i)
+      if (wbase + i * 32 + lane < valid) atomicAdd(&s_cnt[(key[i] >> shift) & MASK], 1u);
+    __syncthreads();
+    // An 8-ary tree of aggregates gives the exclusive prefix over the partitions, per digit.  Level 0 holds one word per
+    // (partition, digit); a level-k word is the sum of an aligned group of 8 words of level k-1, published by whichever
+    // CTA arrives LAST in that group (an arrival counter per group).  A prefix is then <= 7 earlier siblings per level -
+    // words that depend on nobody's prefix.  The usual chained look-back serialises here: a depth sort is ONE wave of
+    // ~500 partitions that all post at the same moment, and the first inclusive value crept forward 8 partitions per
+    // L2 round trip (30 us of a 37 us pass; with every partition resident 110 us).
+    uint32_t total[DPT];
+    {
+      const uint32_t* off = lv.off;
+#pragma unroll
+      for (int j = 0; j < DPT; ++j) {
+        total[j] = s_cnt[tid * DPT + j];
+        st_relaxed(lookback + (static_cast<size_t>(off[0]) + part) * BINS + tid * DPT + j, kFlagAggregate | total[j]);
+      }
+      // climb: the last arriver of a complete group sums it and arrives, in turn, at the group's parent
+      uint32_t idx = part;
+      for (int k = 0; k + 1 < lv.K; ++k) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_arrive = atomicAdd(&counters[off[k + 1] + (idx >> 3)], 1u);
+        __syncthreads();
+        if (s_arrive != 7u) break;  // CTA-uniform; a partial group at the end of a level never completes and is never read
+        __threadfence();
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+          const uint32_t* row = lookback + (static_cast<size_t>(off[k]) + (idx & ~7u)) * BINS + tid * DPT + j;
+          uint32_t w[8], sum = 0;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) w[m] = ld_relaxed(row + static_cast<size_t>(m) * BINS);
+#pragma unroll
+          for (int m = 0; m < 8; ++m) sum += w[m] & kValueMask;
+          st_relaxed(lookback + (static_cast<size_t>(off[k + 1]) + (idx >> 3)) * BINS + tid * DPT + j, kFlagAggregate | sum);
+        }
+        idx >>= 3;
+      }
+    }
+
+    // ---- rank
     uint32_t* wh = s_whist + warp * BINS;
     // lanes holding the same digit, from BITS ballots (match.any costs one round per distinct value in the warp -
     // ~30 of them for a dense digit: it took a quarter of the kernel's stall samples); all 16 items first, so the
@@ -243,8 +291,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) k_sort_onesweep(SortArgs a, i
     }
     __syncthreads();
 
-    // ---- this thread's digits across warps -> per-warp exclusive bases, block totals
-    uint32_t total[DPT];
+    // ---- this thread's digits across warps -> per-warp exclusive bases
 #pragma unroll
     for (int j = 0; j < DPT; ++j) {
       const uint32_t d = tid * DPT + j;
@@ -255,43 +302,13 @@ __global__ void __launch_bounds__(kSortThreads, 4) k_sort_onesweep(SortArgs a, i
         s_whist[w * BINS + d] = t;
         t += c;
       }
-      total[j] = t;
     }
-    // ---- exclusive prefix over the partitions before this one, per digit: an 8-ary tree of aggregates.
-    // Level 0 holds one word per (partition, digit); a level-k word is the sum of an aligned group of 8 words of level
-    // k-1, published by whichever CTA arrives LAST in that group (an arrival counter per group).  A prefix is then
-    // <= 7 earlier siblings per level - words that depend on nobody's prefix.  The usual chained look-back serialises
-    // here: a depth sort is ONE wave of ~500 partitions that all post at the same moment, and the first inclusive
-    // value crept forward 8 partitions per L2 round trip (30 us of a 37 us pass; with every partition resident 110 us).
+    // ---- descend the tree: earlier siblings of this partition's ancestor at every level (posted long ago by now)
     uint32_t excl[DPT];
 #pragma unroll
     for (int j = 0; j < DPT; ++j) excl[j] = 0;
     {
       const uint32_t* off = lv.off;
-#pragma unroll
-      for (int j = 0; j < DPT; ++j)
-        st_relaxed(lookback + (static_cast<size_t>(off[0]) + part) * BINS + tid * DPT + j, kFlagAggregate | total[j]);
-      // climb: the last arriver of a complete group sums it and arrives, in turn, at the group's parent
-      uint32_t idx = part;
-      for (int k = 0; k + 1 < lv.K; ++k) {
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) s_arrive = atomicAdd(&counters[off[k + 1] + (idx >> 3)], 1u);
-        __syncthreads();
-        if (s_arrive != 7u) break;  // CTA-uniform; a partial group at the end of a level never completes and is never read
-        __threadfence();
-#pragma unroll
-        for (int j = 0; j < DPT; ++j) {
-          const uint32_t* row = lookback + (static_cast<size_t>(off[k]) + (idx & ~7u)) * BINS + tid * DPT + j;
-          uint32_t w[8], sum = 0;
-#pragma unroll
-          for (int m = 0; m < 8; ++m) w[m] = ld_relaxed(row + static_cast<size_t>(m) * BINS);
-#pragma unroll
-          for (int m = 0; m < 8; ++m) sum += w[m] & kValueMask;
-          st_relaxed(lookback + (static_cast<size_t>(off[k + 1]) + (idx >> 3)) * BINS + tid * DPT + j, kFlagAggregate | sum);
-        }
-        idx >>= 3;
-      }
       // descend: earlier siblings of this partition's ancestor at every level
       for (int k = 0; k < lv.K; ++k) {
         const uint32_t me = part >> (3 * k), nsib = me & 7u;
