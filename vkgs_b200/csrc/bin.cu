@@ -397,7 +397,15 @@ k_bin_place(const FrameParams* __restrict__ fpp, const Control* __restrict__ ctr
       const uint32_t e = e0 + lane;
       const bool valid = e < w_hi;
       const uint32_t bin = valid ? bin_of(sh.rect[rank], e - sh.off[rank], cbins_x) : 0xffffffffu;
-      const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+      // lanes with the same bin, from 8 ballots (bins < 256): match.any costs a round per distinct value in the warp,
+      // and 32 consecutive pairs of depth-ordered splats land in ~20 different bins
+      uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const bool bit = (bin >> b) & 1u;
+        const uint32_t v = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? v : ~v;
+      }
       const uint32_t leader = __ffs(peers) - 1;
       uint32_t prev = 0;
       if (valid && lane == leader) {
