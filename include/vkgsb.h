@@ -126,6 +126,16 @@ VKGSB_API int vkgsb_upload_splats(vkgsb_renderer* r, uint32_t n, const float* ro
 VKGSB_API int vkgsb_set_camera(vkgsb_renderer* r, const vkgsb_camera* cam);
 VKGSB_API int vkgsb_set_viewport(vkgsb_renderer* r, uint32_t width, uint32_t height);
 
+/* Opaque line layer under the splats: the reference's axis and grid (engine.cc:618-680 geometry, drawn at
+ * engine.cc:1440-1469 through color.vert/.frag with a LINE_LIST pipeline that tests AND writes depth,
+ * engine.cc:398-415).  The lines are drawn first; the splats are then depth-tested LESS against them without writing
+ * depth (engine.cc:298-299) - the reason the reference keeps a graphics pipeline at all (DETAILS.md:7).
+ * positions: 2 * n_lines xyz; colors: 2 * n_lines straight-alpha rgba (color.frag premultiplies); model: the lines' own
+ * push constant, column-major (engine.cc:1444-1448 uses diag(10, 10, 10, 1)); NULL = identity.  All host pointers,
+ * copied.  n_lines = 0 removes the layer (the default: frames then cost exactly what they did without it). */
+VKGSB_API int vkgsb_set_lines(vkgsb_renderer* r, uint32_t n_lines, const float* positions, const float* colors,
+                              const float model[16]);
+
 /* One frame: rank -> sort -> projection -> draw (engine.cc:1164-1290), into an RGBA8/BGRA8 image of
  * width*height*4 bytes.  dst may be NULL (image stays in the renderer, see vkgsb_image_device_ptr), a host pointer
  * (dst_is_device = 0: device->host copy, returns when the pixels are in dst) or a device pointer (dst_is_device = 1:

@@ -142,6 +142,30 @@ def raster_rows(inst: np.ndarray, width: int, height: int, row0: int, row1: int,
     return out
 
 
+def raster_lines(positions, colors, pvm, width: int, height: int):
+    """The opaque line layer (axis / grid of the reference viewer): (depth f32 [H,W], rgba u8 [H,W,4])."""
+    pos = _f32(positions).reshape(-1, 6)
+    col = _f32(colors).reshape(-1, 8)
+    assert pos.shape[0] == col.shape[0]
+    pvm = _f32(pvm).reshape(16)
+    depth = np.empty((height, width), np.float32)
+    rgba = np.empty((height, width, 4), np.uint8)
+    lib().vko_raster_lines(C.c_uint32(pos.shape[0]), _p(pos), _p(col), _p(pvm), C.c_uint32(width), C.c_uint32(height),
+                           _p(depth), _p(rgba))
+    return depth, rgba
+
+
+def raster_layer(inst: np.ndarray, width: int, height: int, layer_depth, layer_rgba, mode: int = 0, tile: int = 16):
+    """Splats over an opaque layer: depth-tested LESS against layer_depth, blended over layer_rgba."""
+    inst = _f32(inst).reshape(-1, 12)
+    out = np.zeros((height, width, 4), np.uint8)
+    ld = _f32(layer_depth).reshape(height, width)
+    lc = np.ascontiguousarray(layer_rgba, np.uint8).reshape(height, width, 4)
+    lib().vko_raster_rows_layer(C.c_uint32(inst.shape[0]), _p(inst), C.c_uint32(width), C.c_uint32(height), C.c_uint32(tile),
+                                C.c_int(mode), C.c_uint32(0), C.c_uint32(height), _p(ld), _p(lc), _p(out), None)
+    return out
+
+
 def render(scene: Scene, cam: Camera, mode: int = 0, tile: int = 16):
     """Whole frame; returns dict(image, keys, ids, inst, stats)."""
     keys = np.empty(scene.n, np.uint32); ids = np.empty(scene.n, np.uint32)

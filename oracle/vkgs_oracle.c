@@ -410,7 +410,7 @@ VKO_API void vko_project(uint32_t v, const uint32_t* ids, const float* pos, cons
  * out: RGBA8, row-major, y down.  Optional fout = un-quantised fp32 RGBA (mode 0 only).
  */
 typedef struct {
-  float cpx, cpy, a00, a01, a10, a11, r, g, b, op;
+  float cpx, cpy, a00, a01, a10, a11, r, g, b, op, z;
   int x0, x1, y0, y1; /* inclusive pixel bbox, clipped; x0>x1 => nothing */
 } raster_splat;
 
@@ -418,6 +418,7 @@ static void raster_setup(const float* inst, uint32_t W, uint32_t H, raster_splat
   float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
   s->x0 = 1; s->x1 = 0; s->y0 = 1; s->y1 = 0;
   if (!(inst[2] < 1.f)) return; /* depth LESS vs cleared 1.0 */
+  s->z = inst[2];
   s->cpx = fmaf(inst[0], hw, hw - 0.5f);
   s->cpy = fmaf(inst[1], hh, hh - 0.5f);
   float m00 = inst[4] * hw, m10 = inst[5] * hh, m01 = inst[6] * hw, m11 = inst[7] * hh; /* m[r][c] */
@@ -449,9 +450,119 @@ static inline uint8_t q8(float x) {
   return (uint8_t)v;
 }
 
-/* Rows outside [row0,row1) (rounded outwards to whole tile bands) are left untouched in out. */
-VKO_API void vko_raster_rows(uint32_t v, const float* inst, uint32_t W, uint32_t H, uint32_t tile, int mode,
-                             uint32_t row0, uint32_t row1, uint8_t* out, float* fout) {
+/* ---------------------------------------------------------------- opaque line layer
+ * The reference draws its axis and grid lines BEFORE the splats with depth test and depth write (engine.cc:1440-1469,
+ * pipeline state engine.cc:398-415: LINE_LIST; color.vert: gl_Position = projection * view * model * position;
+ * color.frag: premultiplied colour), then the splats with depth test LESS and no depth write (engine.cc:298-299): a
+ * splat fragment behind a line pixel is discarded, the rest blend over the line colour.
+ * Vulkan leaves non-strict line rasterisation to the implementation (and the reference has no test for it): PARITY
+ * UNPINNED.  The rule pinned here and in csrc/lines.cu, operation for operation:
+ *   clip-space endpoints by the fma chains of mat4_vec; parametric clip against the six frustum planes (t = d0/(d0-d1));
+ *   NDC by one reciprocal of w; screen x = fma(ndc.x, W/2, W/2) (pixel i covers [i, i+1)), likewise y;
+ *   walk the major axis (|dx| >= |dy| ? x : y) from the smaller to the larger coordinate: every pixel whose centre
+ *   c + 0.5 lies in [a0, a1) gets one fragment at u = ((c + 0.5) - a0) * (1 / (a1 - a0)), minor = floor(fma(u, dm, m0)),
+ *   depth = fma(u, dz, z0), colour = fma(u, dc, c0) premultiplied and rounded to UNORM8 (the target's format);
+ *   depth test LESS with write: the nearest fragment of a pixel wins, equal depths by the smaller packed colour.
+ * layer_depth: W*H floats, 1.0 where no line; layer_rgba: W*H*4 bytes, (0,0,0,255) (the clear colour) where no line. */
+static inline uint8_t q8(float x);
+VKO_API void vko_raster_lines(uint32_t n_lines, const float* pos /* 2n x 3 */, const float* col /* 2n x 4 */,
+                              const float* pvm /* proj*view*model of the lines */, uint32_t W, uint32_t H,
+                              float* layer_depth, uint8_t* layer_rgba) {
+  for (size_t i = 0; i < (size_t)W * H; ++i) {
+    layer_depth[i] = 1.f;
+    layer_rgba[4 * i + 0] = 0; layer_rgba[4 * i + 1] = 0; layer_rgba[4 * i + 2] = 0; layer_rgba[4 * i + 3] = 255;
+  }
+  uint64_t* best = (uint64_t*)malloc((size_t)W * H * sizeof(uint64_t));
+  for (size_t i = 0; i < (size_t)W * H; ++i) best[i] = ~0ull;
+  const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+  for (uint32_t l = 0; l < n_lines; ++l) {
+    float p0[4] = {pos[6 * l + 0], pos[6 * l + 1], pos[6 * l + 2], 1.f}, p1[4] = {pos[6 * l + 3], pos[6 * l + 4], pos[6 * l + 5], 1.f};
+    float c0[4], c1[4];
+    mat4_vec(pvm, p0, c0);
+    mat4_vec(pvm, p1, c1);
+    float t0 = 0.f, t1 = 1.f;
+    int reject = 0;
+    for (int pl = 0; pl < 6 && !reject; ++pl) {
+      float d0, d1;
+      switch (pl) {
+        case 0: d0 = c0[3] + c0[0]; d1 = c1[3] + c1[0]; break;
+        case 1: d0 = c0[3] - c0[0]; d1 = c1[3] - c1[0]; break;
+        case 2: d0 = c0[3] + c0[1]; d1 = c1[3] + c1[1]; break;
+        case 3: d0 = c0[3] - c0[1]; d1 = c1[3] - c1[1]; break;
+        case 4: d0 = c0[2]; d1 = c1[2]; break;
+        default: d0 = c0[3] - c0[2]; d1 = c1[3] - c1[2]; break;
+      }
+      if (d0 < 0.f && d1 < 0.f) { reject = 1; break; }
+      if (!(d0 == d0) || !(d1 == d1)) { reject = 1; break; }
+      if (d0 < 0.f) { float t = d0 / (d0 - d1); if (t > t0) t0 = t; }
+      else if (d1 < 0.f) { float t = d0 / (d0 - d1); if (t < t1) t1 = t; }
+    }
+    if (reject || !(t0 < t1)) continue;
+    float e0[4], e1[4];
+    for (int k = 0; k < 4; ++k) {
+      float d = c1[k] - c0[k];
+      e0[k] = fmaf(t0, d, c0[k]);
+      e1[k] = fmaf(t1, d, c0[k]);
+    }
+    /* premultiplied colours at the clipped ends */
+    float q0[4], q1[4];
+    for (int k = 0; k < 4; ++k) {
+      float a = col[8 * l + k], b = col[8 * l + 4 + k], d = b - a;
+      q0[k] = fmaf(t0, d, a);
+      q1[k] = fmaf(t1, d, a);
+    }
+    for (int k = 0; k < 3; ++k) { q0[k] = q0[k] * q0[3]; q1[k] = q1[k] * q1[3]; }
+    float iw0 = 1.f / e0[3], iw1 = 1.f / e1[3];
+    float sx0 = fmaf(e0[0] * iw0, hw, hw), sy0 = fmaf(e0[1] * iw0, hh, hh), z0 = e0[2] * iw0;
+    float sx1 = fmaf(e1[0] * iw1, hw, hw), sy1 = fmaf(e1[1] * iw1, hh, hh), z1 = e1[2] * iw1;
+    int xmajor = fabsf(sx1 - sx0) >= fabsf(sy1 - sy0);
+    float a0 = xmajor ? sx0 : sy0, a1 = xmajor ? sx1 : sy1, m0 = xmajor ? sy0 : sx0, m1 = xmajor ? sy1 : sx1;
+    if (a0 > a1) { /* walk from the smaller major coordinate */
+      float t;
+      t = a0; a0 = a1; a1 = t;
+      t = m0; m0 = m1; m1 = t;
+      t = z0; z0 = z1; z1 = t;
+      for (int k = 0; k < 4; ++k) { t = q0[k]; q0[k] = q1[k]; q1[k] = t; }
+    }
+    if (!(a1 > a0)) continue; /* degenerate (or NaN) */
+    float inv = 1.f / (a1 - a0), dm = m1 - m0, dz = z1 - z0;
+    float lim_a = xmajor ? (float)W : (float)H;
+    float fa = ceilf(a0 - 0.5f), fb = ceilf(a1 - 0.5f) - 1.f; /* centres c + 0.5 in [a0, a1) */
+    if (fa < 0.f) fa = 0.f;
+    if (fb > lim_a - 1.f) fb = lim_a - 1.f;
+    if (!(fa <= fb)) continue;
+    int ca = (int)fa, cb = (int)fb, lim_m = xmajor ? (int)H : (int)W;
+    for (int c = ca; c <= cb; ++c) {
+      float u = (((float)c + 0.5f) - a0) * inv;
+      float mf = floorf(fmaf(u, dm, m0));
+      if (!(mf >= 0.f && mf <= (float)(lim_m - 1))) continue;
+      int m = (int)mf;
+      float z = fmaf(u, dz, z0);
+      if (!(z >= 0.f && z <= 1.f)) continue;
+      uint32_t rgba = 0;
+      for (int k = 0; k < 4; ++k) rgba |= (uint32_t)q8(fmaf(u, q1[k] - q0[k], q0[k])) << (8 * k);
+      uint64_t packed = ((uint64_t)f2u(z) << 32) | rgba;
+      size_t pix = xmajor ? (size_t)m * W + (size_t)c : (size_t)c * W + (size_t)m;
+      if (packed < best[pix]) best[pix] = packed;
+    }
+  }
+  for (size_t i = 0; i < (size_t)W * H; ++i)
+    if (best[i] != ~0ull) {
+      uint32_t zb = (uint32_t)(best[i] >> 32), rgba = (uint32_t)best[i];
+      memcpy(&layer_depth[i], &zb, 4);
+      /* premultiplied source over the clear colour (0,0,0,1), ONE / ONE_MINUS_SRC_ALPHA: rgb stays, alpha -> 1 */
+      layer_rgba[4 * i + 0] = (uint8_t)rgba; layer_rgba[4 * i + 1] = (uint8_t)(rgba >> 8);
+      layer_rgba[4 * i + 2] = (uint8_t)(rgba >> 16); layer_rgba[4 * i + 3] = 255;
+    }
+  free(best);
+}
+
+/* Rows outside [row0,row1) (rounded outwards to whole tile bands) are left untouched in out.
+ * layer_depth / layer_rgba (both NULL, or both W*H): the opaque layer under the splats - the accumulators start from its
+ * colour and a fragment is kept only if ndc.z < layer_depth (depth test LESS, no write). */
+VKO_API void vko_raster_rows_layer(uint32_t v, const float* inst, uint32_t W, uint32_t H, uint32_t tile, int mode,
+                                   uint32_t row0, uint32_t row1, const float* layer_depth, const uint8_t* layer_rgba,
+                                   uint8_t* out, float* fout) {
   raster_splat* S = (raster_splat*)malloc((size_t)(v ? v : 1) * sizeof(raster_splat));
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)v; ++i) raster_setup(inst + 12 * i, W, H, &S[i]);
@@ -468,6 +579,10 @@ VKO_API void vko_raster_rows(uint32_t v, const float* inst, uint32_t W, uint32_t
     for (size_t k = 0; k < npx; ++k) {
       acc[4 * k + 0] = 0.f; acc[4 * k + 1] = 0.f; acc[4 * k + 2] = 0.f;
       acc[4 * k + 3] = mode == 1 ? 255.f : 1.f;
+      if (layer_rgba) { /* the target holds UNORM8 values when the splats start */
+        const uint8_t* lc = layer_rgba + 4 * ((size_t)by0 * W + k);
+        for (int ch = 0; ch < 4; ++ch) acc[4 * k + ch] = mode == 1 ? (float)lc[ch] : (float)lc[ch] / 255.f;
+      }
     }
     for (uint32_t i = 0; i < v; ++i) {
       const raster_splat* s = &S[i];
@@ -490,6 +605,7 @@ VKO_API void vko_raster_rows(uint32_t v, const float* inst, uint32_t W, uint32_t
             float lx = (float)(xx - tx);
             float px = fmaf(s->a00, lx, ex), py = fmaf(s->a10, lx, ey);
             if (!(fabsf(px) <= 3.f && fabsf(py) <= 3.f)) continue;
+            if (layer_depth && !(s->z < layer_depth[(size_t)yy * W + xx])) continue; /* depth test LESS */
             float al = s->op * expf(-0.5f * fmaf(py, py, px * px));
             if (al > 1.f) al = 1.f;
             if (!(al >= 0.f)) al = 0.f;
@@ -524,6 +640,11 @@ VKO_API void vko_raster_rows(uint32_t v, const float* inst, uint32_t W, uint32_t
     free(acc);
   }
   free(S);
+}
+
+VKO_API void vko_raster_rows(uint32_t v, const float* inst, uint32_t W, uint32_t H, uint32_t tile, int mode,
+                             uint32_t row0, uint32_t row1, uint8_t* out, float* fout) {
+  vko_raster_rows_layer(v, inst, W, H, tile, mode, row0, row1, NULL, NULL, out, fout);
 }
 
 VKO_API void vko_raster(uint32_t v, const float* inst, uint32_t W, uint32_t H, uint32_t tile, int mode,

@@ -49,6 +49,7 @@ SIGNATURES = {
     "vkgsb_upload_splats": (C.c_int, [_P, C.c_uint32, _P, _P]),
     "vkgsb_set_camera": (C.c_int, [_P, C.POINTER(CameraBlock)]),
     "vkgsb_set_viewport": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "vkgsb_set_lines": (C.c_int, [_P, C.c_uint32, _P, _P, _P]),
     "vkgsb_draw": (C.c_int, [_P, _P, C.c_int, _P]),
     "vkgsb_draw_batch": (C.c_int, [_P, C.c_uint32, C.POINTER(CameraBlock), _P, C.c_size_t, C.c_int, _P]),
     "vkgsb_image_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),

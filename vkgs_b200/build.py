@@ -30,6 +30,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-I", os.path.join(ROOT, "include"),
 SOURCES = {
     "project.cu": ["-fmad=false"] + os.environ.get("VKGSB_PROJECT_FLAGS", "").split(),
     "load.cu": ["-fmad=false"],
+    "lines.cu": ["-fmad=false"],
     "sort.cu": [],
     "bin.cu": [],
     "blend.cu": [],

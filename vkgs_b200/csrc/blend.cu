@@ -27,6 +27,7 @@ constexpr int kBatch = 1024;
 constexpr int kPix = 4;  // pixels per lane: rows ly0 + 2k of a 16x8 sub-tile
 constexpr float kTransmittanceCut = 1e-4f;
 constexpr size_t kBlendSmem = kBatch * (3 * sizeof(float4) + sizeof(uint32_t));
+constexpr size_t kBlendSmemLayer = kBlendSmem + kBatch * sizeof(float);  // + ndc.z of the staged entries
 
 __device__ __forceinline__ uint32_t quantize8(float x) {  // RNE, saturating
   return static_cast<uint32_t>(__float2int_rn(__saturatef(x) * 255.f));
@@ -52,15 +53,20 @@ __device__ __forceinline__ uint32_t subtile_mask(uint32_t x0, uint32_t x1, uint3
   return rows * cols;  // no carries: cols <= 0xF
 }
 
-template <int MODE>
+// LAYER: an opaque line layer lies under the splats (lines.cu; the reference's axis / grid, engine.cc:1440-1469).  A
+// fragment is kept only if the splat's ndc.z is LESS than the layer's depth at the pixel (engine.cc:298-299), and the
+// result is composited over the layer's colour instead of the clear colour.
+template <int MODE, bool LAYER>
 __global__ void __launch_bounds__(kBlendThreads, 1)
 k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ pair_rank,
-        const float4* __restrict__ rrec, int bgra, uint8_t* __restrict__ image) {
+        const float4* __restrict__ rrec, int bgra, const unsigned long long* __restrict__ layer,
+        const float* __restrict__ zndc, uint8_t* __restrict__ image) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float4* s_q0 = reinterpret_cast<float4*>(smem_raw);
   float4* s_q1 = s_q0 + kBatch;
   float4* s_q2 = s_q1 + kBatch;
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_q2 + kBatch);
+  float* s_z = reinterpret_cast<float*>(s_mask + kBatch);  // LAYER only
   __shared__ uint32_t s_alive;
 
   const uint32_t width = fpp->width, bins_x = fpp->bins_x;
@@ -79,6 +85,20 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
     const uint32_t y = y_first + 2 * k;
     fly[k] = static_cast<float>(y - org_y);
     inside[k] = x < width && y >= band_y0 && y < band_y1;
+  }
+  float ldepth[kPix];   // the layer's depth at the pixel (1.0 = cleared: every splat with ndc.z < 1 passes)
+  uint32_t lrgba[kPix]; // and its colour; (0,0,0,255) = the clear colour (engine.cc:1382-1387)
+#pragma unroll
+  for (int k = 0; k < kPix; ++k) {
+    ldepth[k] = 1.f;
+    lrgba[k] = 0xff000000u;
+    if (LAYER && inside[k]) {
+      const unsigned long long w = __ldg(layer + static_cast<size_t>(y_first + 2 * k) * width + x);
+      if (w != ~0ull) {
+        ldepth[k] = __uint_as_float(static_cast<uint32_t>(w >> 32));
+        lrgba[k] = static_cast<uint32_t>(w) | 0xff000000u;  // premultiplied over the opaque clear colour: alpha -> 1
+      }
+    }
   }
   uint2 range = ranges[((bin_y >> fpp->cshift_y) - fpp->cbin_y0) * fpp->cbins_x + (bin_x >> fpp->cshift_x)];
   if (range.y < range.x) range.y = range.x;  // a bin no pair reached keeps end = 0 (bin.cu)
@@ -107,6 +127,7 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
         const float4 q0 = __ldg(rrec + rank * 3 + 0), q1 = __ldg(rrec + rank * 3 + 1), q2 = __ldg(rrec + rank * 3 + 2);
         const uint32_t bxw = __float_as_uint(q2.z), byw = __float_as_uint(q2.w);
         s_q0[tid] = q0; s_q1[tid] = q1; s_q2[tid] = q2;
+        if (LAYER) s_z[tid] = __ldg(zndc + rank);
         s_mask[tid] = subtile_mask(bxw & 0xffffu, bxw >> 16, byw & 0xffffu, byw >> 16, bin_x, bin_y) & alive;
       }
       __syncthreads();
@@ -122,11 +143,12 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
             const float ox = __fsub_rn(tile_x, q1.x), oy = __fsub_rn(tile_y, q1.y);
             const float bx = __fadd_rn(__fmul_rn(q0.x, ox), __fmul_rn(q0.y, oy));
             const float by = __fadd_rn(__fmul_rn(q0.z, ox), __fmul_rn(q0.w, oy));
+            const float z = LAYER ? s_z[j] : 0.f;
 #pragma unroll
             for (int k = 0; k < kPix; ++k) {
               const float px = fmaf(q0.x, flx, fmaf(q0.y, fly[k], bx));
               const float py = fmaf(q0.z, flx, fmaf(q0.w, fly[k], by));
-              if (!done[k] && fabsf(px) <= 3.f && fabsf(py) <= 3.f) {
+              if (!done[k] && fabsf(px) <= 3.f && fabsf(py) <= 3.f && (!LAYER || z < ldepth[k])) {
                 const float al = __saturatef(q2.y * __expf(-0.5f * fmaf(py, py, px * px)));
                 const float w = al * T[k];
                 cr[k] = fmaf(q1.z, w, cr[k]);
@@ -150,14 +172,25 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
     uint32_t* img = reinterpret_cast<uint32_t*>(image);
 #pragma unroll
     for (int k = 0; k < kPix; ++k)
-      if (inside[k])
+      if (inside[k]) {
+        if (LAYER) {  // what is left of the transmittance shows the layer (UNORM8 in the target when the splats start)
+          cr[k] = fmaf(static_cast<float>(lrgba[k] & 255u) * (1.f / 255.f), T[k], cr[k]);
+          cg[k] = fmaf(static_cast<float>((lrgba[k] >> 8) & 255u) * (1.f / 255.f), T[k], cg[k]);
+          cb[k] = fmaf(static_cast<float>((lrgba[k] >> 16) & 255u) * (1.f / 255.f), T[k], cb[k]);
+        }
         img[static_cast<size_t>(y_first + 2 * k) * width + x] =
             pack_pixel(quantize8(cr[k]), quantize8(cg[k]), quantize8(cb[k]), quantize8(ca[k] + T[k]), bgra);
+      }
   } else {
     // back-to-front over the nearest-first list: batches from the tail, entries in reverse
     float qr[kPix], qg[kPix], qb[kPix], qa[kPix];
 #pragma unroll
-    for (int k = 0; k < kPix; ++k) { qr[k] = qg[k] = qb[k] = 0.f; qa[k] = 255.f; }
+    for (int k = 0; k < kPix; ++k) {
+      qr[k] = static_cast<float>(lrgba[k] & 255u);
+      qg[k] = static_cast<float>((lrgba[k] >> 8) & 255u);
+      qb[k] = static_cast<float>((lrgba[k] >> 16) & 255u);
+      qa[k] = 255.f;
+    }
     uint32_t remaining = range.y - range.x;
     while (remaining > 0) {
       const uint32_t cnt = min(static_cast<uint32_t>(kBatch), remaining);
@@ -168,6 +201,7 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
         const float4 q0 = __ldg(rrec + rank * 3 + 0), q1 = __ldg(rrec + rank * 3 + 1), q2 = __ldg(rrec + rank * 3 + 2);
         const uint32_t bxw = __float_as_uint(q2.z), byw = __float_as_uint(q2.w);
         s_q0[tid] = q0; s_q1[tid] = q1; s_q2[tid] = q2;
+        if (LAYER) s_z[tid] = __ldg(zndc + rank);
         s_mask[tid] = subtile_mask(bxw & 0xffffu, bxw >> 16, byw & 0xffffu, byw >> 16, bin_x, bin_y);
       }
       __syncthreads();
@@ -184,11 +218,12 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
           const float bx = __fadd_rn(__fmul_rn(q0.x, ox), __fmul_rn(q0.y, oy));
           const float by = __fadd_rn(__fmul_rn(q0.z, ox), __fmul_rn(q0.w, oy));
           const float r255 = __fmul_rn(255.f, q1.z), g255 = __fmul_rn(255.f, q1.w), b255 = __fmul_rn(255.f, q2.x);
+          const float z = LAYER ? s_z[j] : 0.f;
 #pragma unroll
           for (int k = 0; k < kPix; ++k) {
             const float px = fmaf(q0.x, flx, fmaf(q0.y, fly[k], bx));
             const float py = fmaf(q0.z, flx, fmaf(q0.w, fly[k], by));
-            if (fabsf(px) <= 3.f && fabsf(py) <= 3.f) {
+            if (fabsf(px) <= 3.f && fabsf(py) <= 3.f && (!LAYER || z < ldepth[k])) {
               const float al = __saturatef(q2.y * __expf(-0.5f * fmaf(py, py, px * px)));
               const float om = __fsub_rn(1.f, al);
               qr[k] = rintf(fmaf(r255, al, __fmul_rn(qr[k], om)));
@@ -211,20 +246,34 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
 }
 
 void blend_configure() {
-  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_FP32_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmem);
-  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_UNORM8_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmem);
+  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_FP32_MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmem);
+  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_UNORM8_MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmem);
+  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_FP32_MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmemLayer);
+  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_UNORM8_MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmemLayer);
 }
 
 void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_rank,
-                  const float* d_rrec, int blend_mode, int bgra, uint8_t* d_image, cudaStream_t stream) {
+                  const float* d_rrec, int blend_mode, int bgra, const unsigned long long* d_layer, const float* d_zndc,
+                  uint8_t* d_image, cudaStream_t stream) {
   const uint32_t nbins = h_fp.bins_x * (h_fp.bin_y1 - h_fp.bin_y0);
   if (nbins == 0) return;
-  if (blend_mode == VKGSB_BLEND_FP32_MODE)
-    k_blend<VKGSB_BLEND_FP32_MODE><<<nbins, kBlendThreads, kBlendSmem, stream>>>(
-        d_fp, d_ranges, d_pair_rank, reinterpret_cast<const float4*>(d_rrec), bgra, d_image);
-  else
-    k_blend<VKGSB_BLEND_UNORM8_MODE><<<nbins, kBlendThreads, kBlendSmem, stream>>>(
-        d_fp, d_ranges, d_pair_rank, reinterpret_cast<const float4*>(d_rrec), bgra, d_image);
+  const float4* rrec = reinterpret_cast<const float4*>(d_rrec);
+  const bool layer = d_layer != nullptr && d_zndc != nullptr;
+  if (blend_mode == VKGSB_BLEND_FP32_MODE) {
+    if (layer)
+      k_blend<VKGSB_BLEND_FP32_MODE, true><<<nbins, kBlendThreads, kBlendSmemLayer, stream>>>(
+          d_fp, d_ranges, d_pair_rank, rrec, bgra, d_layer, d_zndc, d_image);
+    else
+      k_blend<VKGSB_BLEND_FP32_MODE, false><<<nbins, kBlendThreads, kBlendSmem, stream>>>(
+          d_fp, d_ranges, d_pair_rank, rrec, bgra, nullptr, nullptr, d_image);
+  } else {
+    if (layer)
+      k_blend<VKGSB_BLEND_UNORM8_MODE, true><<<nbins, kBlendThreads, kBlendSmemLayer, stream>>>(
+          d_fp, d_ranges, d_pair_rank, rrec, bgra, d_layer, d_zndc, d_image);
+    else
+      k_blend<VKGSB_BLEND_UNORM8_MODE, false><<<nbins, kBlendThreads, kBlendSmem, stream>>>(
+          d_fp, d_ranges, d_pair_rank, rrec, bgra, nullptr, nullptr, d_image);
+  }
 }
 
 }  // namespace vkgsb

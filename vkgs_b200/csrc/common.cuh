@@ -15,6 +15,8 @@ constexpr int kTile = 16;              // origin granularity of the pinned fragm
 // (4 pixels per lane).
 constexpr int kBinW = 64, kBinH = 64, kSubW = 16, kSubH = 8;
 constexpr uint32_t kFlagKeepInstances = 1u;  // also write the reference-format instance records (parity tap)
+constexpr uint32_t kFlagDepthLayer = 2u;     // an opaque line layer is drawn under the splats (lines.cu): k_project also
+                                             // writes ndc.z per slot, the blend stage depth-tests against the layer
 constexpr int kSubCols = kBinW / kSubW, kSubRows = kBinH / kSubH;  // 4 x 8 = 32 sub-tiles
 constexpr int kMaxCoarseBins = 256;
 constexpr int kMaxImageDim = 8192;
@@ -63,6 +65,7 @@ struct FrameParams {
   uint32_t cbin_y0;             // first coarse row of the band
   uint32_t ncbins;              // coarse bins covering the band: cbins_x * rows (<= kMaxCoarseBins)
   uint32_t pad1[3];
+  float pvm_lines[16];          // (proj*view)*model of the line layer (color.vert, engine.cc:1444-1448)
 };
 
 // ---- control block: everything the host zeroes with one memset per frame --------------------------------------

@@ -30,7 +30,7 @@ uint32_t project_num_tiles(uint32_t n);  // scan descriptors k_project needs
 // FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control.
 void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl, unsigned long long* d_scan_desc,
                     uint32_t* d_keys, uint32_t* d_slots, uint32_t* d_vis_id, float* d_rrec, uint32_t* d_bin_rect,
-                    float* d_inst, cudaStream_t stream);
+                    float* d_inst, float* d_zndc, cudaStream_t stream);
 
 // ---- sort.cu: onesweep LSD radix sort, count read on the device ----------------------------------------------------
 struct SortArgs {
@@ -75,9 +75,15 @@ void launch_bin(const FrameParams* d_fp, uint32_t ncbins, Control* d_ctrl, const
 
 // ---- blend.cu ------------------------------------------------------------------------------------------------------
 void blend_configure();  // once per device: opt in to > 48 KB dynamic shared memory
+// ---- lines.cu: opaque line layer (depth bits << 32 | rgba8 per pixel; all ones = no line) --------------------------
+void launch_lines(const FrameParams* d_fp, uint32_t n_lines, const float* d_pos, const float* d_col, uint32_t width,
+                  uint32_t height, unsigned long long* d_layer, cudaStream_t stream);
+
 // d_ranges: [begin,end) of every coarse bin in d_pair_slot
+// d_layer / d_zndc: both null, or the line layer and the splats' ndc.z by slot (depth test LESS against the layer)
 void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_slot,
-                  const float* d_rrec, int blend_mode, int bgra, uint8_t* d_image, cudaStream_t stream);
+                  const float* d_rrec, int blend_mode, int bgra, const unsigned long long* d_layer, const float* d_zndc,
+                  uint8_t* d_image, cudaStream_t stream);
 
 // ---- misc ----------------------------------------------------------------------------------------------------------
 void launch_gather_sorted(const Control* d_ctrl, const uint32_t* d_sorted_slots, const uint32_t* d_vis_id,

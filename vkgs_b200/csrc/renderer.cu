@@ -60,6 +60,11 @@ struct vkgsb_renderer {
   uint32_t *keys = nullptr, *slots = nullptr, *keys_alt = nullptr, *slots_alt = nullptr, *vis_id = nullptr;
   float* inst = nullptr;
   float* rrec = nullptr;       // raster records by compacted slot (project.cu)
+  // opaque line layer (vkgsb_set_lines): geometry, the per-pixel depth | colour words, the splats' ndc.z by slot
+  uint32_t n_lines = 0;
+  float *line_pos = nullptr, *line_col = nullptr, *zndc = nullptr;
+  unsigned long long* layer = nullptr;
+  float line_model[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   uint32_t* bin_rect = nullptr;  // coarse-bin box by compacted slot
   uint32_t* bin_slots = nullptr;   // splat slots by coarse bin, nearest first (bin.cu); capacity max_pairs
   BinScratch bin{};
@@ -257,7 +262,8 @@ void fill_params(vkgsb_renderer* r) {
   p.cam_model[2] = cm[2] / cm[3];
   p.width = r->width;
   p.height = r->height;
-  p.flags = r->keep_instances ? kFlagKeepInstances : 0u;
+  p.flags = (r->keep_instances ? kFlagKeepInstances : 0u) | (r->n_lines ? kFlagDepthLayer : 0u);
+  mat4_mul(pv, r->line_model, p.pvm_lines);  // projection * view * model of the lines (color.vert)
   p.pad0 = 0u;
   p.bins_x = (r->width + kBinW - 1) / kBinW;
   p.bins_y = (r->height + kBinH - 1) / kBinH;
@@ -290,9 +296,11 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   CU_TRY(cudaMemsetAsync(r->zero_region, 0, r->zero_bytes, s));
   // look-back words of the depth sort: only partitions of the <= n visible splats can be touched
   CU_TRY(cudaMemsetAsync(r->lookback_depth, 0, sort_lookback_bytes(n), s));
+  if (r->n_lines) launch_lines(r->d_fp, r->n_lines, r->line_pos, r->line_col, r->width, r->height, r->layer, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[0], s));
   // the depth sort runs an odd number of passes: its input goes to the ping-pong side, its result lands in keys / slots
-  launch_project(sc, r->d_fp, r->ctrl, r->desc_project, r->keys_alt, r->slots_alt, r->vis_id, r->rrec, r->bin_rect, r->inst, s);
+  launch_project(sc, r->d_fp, r->ctrl, r->desc_project, r->keys_alt, r->slots_alt, r->vis_id, r->rrec, r->bin_rect, r->inst,
+                 r->n_lines ? r->zndc : nullptr, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
   SortArgs depth{};
   depth.d_count = &r->ctrl->visible_count;
@@ -311,7 +319,8 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   launch_bin(r->d_fp, r->h_fp.ncbins, r->ctrl, r->slots, r->bin_rect, n, r->max_pairs, r->bin, r->ranges, r->bin_slots, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[3], s));
   launch_blend(r->d_fp, r->h_fp, r->ranges, r->bin_slots, r->rrec, r->blend_mode,
-               r->pixel_format == VKGSB_FORMAT_BGRA8, r->image, s);
+               r->pixel_format == VKGSB_FORMAT_BGRA8, r->n_lines ? r->layer : nullptr, r->n_lines ? r->zndc : nullptr,
+               r->image, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[4], s));
   CU_TRY(cudaMemcpyAsync(r->h_counts, r->ctrl, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaGetLastError());
@@ -471,7 +480,7 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
                  r->vis_id, r->inst, r->rrec, r->bin_rect, r->bin_slots, r->bin.tile_pairs, r->bin.tile_item, r->bin.tile_bin, r->bin.bin_total,
                  r->lookback_depth, r->zero_region, r->d_fp, r->image, r->stage[0], r->stage[1], r->d_offsets, r->d_rows[0],
-                 r->d_rows[1]};
+                 r->d_rows[1], r->line_pos, r->line_col, r->zndc, r->layer};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (r->h_counts) cudaFreeHost(r->h_counts);
@@ -588,6 +597,32 @@ int vkgsb_set_viewport(vkgsb_renderer* r, uint32_t width, uint32_t height) {
     r->height = height;
     invalidate_graph(r);
   }
+  return VKGSB_OK;
+}
+
+int vkgsb_set_lines(vkgsb_renderer* r, uint32_t n_lines, const float* positions, const float* colors,
+                    const float model[16]) {
+  if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
+  if (n_lines && (!positions || !colors)) return fail(VKGSB_ERR_INVALID, "null line geometry");
+  if (n_lines > (1u << 20)) return fail(VKGSB_ERR_CAPACITY, "at most 2^20 lines");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  std::lock_guard<std::mutex> g(r->draw_mutex);
+  CU_TRY(cudaStreamSynchronize(r->stream));  // frames in flight still read the old geometry
+  invalidate_graph(r);
+  if (r->line_pos) cudaFree(r->line_pos);
+  if (r->line_col) cudaFree(r->line_col);
+  r->line_pos = r->line_col = nullptr;
+  r->n_lines = 0;
+  if (n_lines == 0) return VKGSB_OK;
+  if (!r->layer) CU_TRY(cudaMalloc(&r->layer, static_cast<size_t>(r->max_width) * r->max_height * sizeof(unsigned long long)));
+  if (!r->zndc) CU_TRY(cudaMalloc(&r->zndc, static_cast<size_t>(r->max_splats) * sizeof(float)));
+  CU_TRY(cudaMalloc(&r->line_pos, static_cast<size_t>(n_lines) * 6 * sizeof(float)));
+  CU_TRY(cudaMalloc(&r->line_col, static_cast<size_t>(n_lines) * 8 * sizeof(float)));
+  CU_TRY(cudaMemcpy(r->line_pos, positions, static_cast<size_t>(n_lines) * 6 * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(r->line_col, colors, static_cast<size_t>(n_lines) * 8 * sizeof(float), cudaMemcpyHostToDevice));
+  static const float kIdentity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  std::memcpy(r->line_model, model ? model : kIdentity, sizeof(r->line_model));
+  r->n_lines = n_lines;
   return VKGSB_OK;
 }
 

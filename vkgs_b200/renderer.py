@@ -101,6 +101,18 @@ class Renderer:
         cb = block if block is not None else camera_block(proj, view, eye, model)
         L.check(L.lib().vkgsb_set_camera(self._h, C.byref(cb)))
 
+    def set_lines(self, positions=None, colors=None, model=None):
+        """Opaque line layer under the splats (the reference's axis / grid, engine.cc:1440-1469): positions [n, 2, 3],
+        colors [n, 2, 4] straight alpha, model 4x4 column-major (None = identity).  None / empty removes it."""
+        if positions is None or len(positions) == 0:
+            L.check(L.lib().vkgsb_set_lines(self._h, 0, None, None, None))
+            return
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 6)
+        col = np.ascontiguousarray(colors, np.float32).reshape(-1, 8)
+        assert pos.shape[0] == col.shape[0]
+        m = None if model is None else np.ascontiguousarray(model, np.float32).reshape(16)
+        L.check(L.lib().vkgsb_set_lines(self._h, pos.shape[0], _ptr(pos), _ptr(col), _ptr(m) if m is not None else None))
+
     def set_viewport(self, width: int, height: int):
         L.check(L.lib().vkgsb_set_viewport(self._h, int(width), int(height)))
         self.width, self.height = int(width), int(height)
@@ -178,6 +190,28 @@ class Renderer:
         if n:
             L.check(L.lib().vkgsb_read_scene(self._h, _ptr(pos), _ptr(cov), _ptr(op), _ptr(sh), n, C.byref(cnt)))
         return pos, cov, op, sh
+
+
+def reference_overlay(show_axis: bool = True, show_grid: bool = True):
+    """The reference viewer's axis and grid as (positions [n,2,3], colors [n,2,4], model[16]): engine.cc:618-680 geometry,
+    drawn with model = diag(10, 10, 10, 1) (engine.cc:1444-1448)."""
+    pos, col = [], []
+    if show_axis:
+        for axis, c in enumerate(((1, 0, 0, 1), (0, 1, 0, 1), (0, 0, 1, 1))):
+            e = [0.0, 0.0, 0.0]
+            e[axis] = 1.0
+            pos.append([[0, 0, 0], e])
+            col.append([c, c])
+    if show_grid:
+        g = (0.5, 0.5, 0.5, 1.0)
+        for i in range(-10, 11):
+            t = np.float32(i) / np.float32(10)
+            pos.append([[-1, 0, t], [1, 0, t]])
+            col.append([g, g])
+            pos.append([[t, 0, -1], [t, 0, 1]])
+            col.append([g, g])
+    model = np.diag([10.0, 10.0, 10.0, 1.0]).astype(np.float32).T.reshape(16)
+    return (np.asarray(pos, np.float32).reshape(-1, 2, 3), np.asarray(col, np.float32).reshape(-1, 2, 4), model)
 
 
 def device_count() -> int:
