@@ -1,7 +1,7 @@
 // vkgs::Engine - drop-in for the reference's public class (include/vkgs/engine/engine.h:11-26): the same five
 // methods with the same threading contract, implemented on libvkgsb (CUDA, headless) instead of Vulkan + GLFW.
 // Extensions the north-star asks for (the reference has no programmatic camera, viewport or read-back):
-// camera(), SetViewport(), SetModel(), DrawToImage(), stats().
+// camera(), SetViewport(), SetModel(), SetOverlay(), DrawToImage(), stats().
 #ifndef VKGS_ENGINE_ENGINE_H
 #define VKGS_ENGINE_ENGINE_H
 
@@ -43,6 +43,10 @@ class VKGS_API Engine {
   void SetViewport(uint32_t width, uint32_t height);  // default 1600 x 900 (viewer.cc:67)
   void SetModel(const Mat4& model);
   void SetBlendMode(int vkgsb_blend_mode_value);
+  // The viewer's axis and grid (show_axis_ / show_grid_, engine.cc:1664-1665; geometry engine.cc:618-680) drawn under
+  // the splats with depth test + write, the splats depth-tested against them.  Off until asked for: a headless
+  // frame is the splats alone.
+  void SetOverlay(bool show_axis, bool show_grid);
   void WaitForLoad();
   // One frame at the current camera; RGBA8, width*height*4 bytes.
   void DrawToImage(std::vector<uint8_t>* rgba);

@@ -97,6 +97,31 @@ void Engine::SetModel(const Mat4& model) {
 
 void Engine::SetBlendMode(int mode) { vkgsb_set_option(impl_->renderer_, VKGSB_OPT_BLEND_MODE, mode); }
 
+void Engine::SetOverlay(bool show_axis, bool show_grid) {
+  std::vector<float> pos, col;
+  auto line = [&](float x0, float y0, float z0, float x1, float y1, float z1, float r, float g, float b) {
+    const float p[6] = {x0, y0, z0, x1, y1, z1}, c[8] = {r, g, b, 1.f, r, g, b, 1.f};
+    pos.insert(pos.end(), p, p + 6);
+    col.insert(col.end(), c, c + 8);
+  };
+  if (show_axis) {  // engine.cc:618-627
+    line(0, 0, 0, 1, 0, 0, 1, 0, 0);
+    line(0, 0, 0, 0, 1, 0, 0, 1, 0);
+    line(0, 0, 0, 0, 0, 1, 0, 0, 1);
+  }
+  if (show_grid) {  // engine.cc:635-680: 21 + 21 lines on y = 0
+    constexpr int grid_size = 10;
+    for (int i = -grid_size; i <= grid_size; ++i) {
+      const float t = static_cast<float>(i) / grid_size;
+      line(-1.f, 0, t, 1.f, 0, t, 0.5f, 0.5f, 0.5f);
+      line(t, 0, -1.f, t, 0, 1.f, 0.5f, 0.5f, 0.5f);
+    }
+  }
+  const float model[16] = {10, 0, 0, 0, 0, 10, 0, 0, 0, 0, 10, 0, 0, 0, 0, 1};  // engine.cc:1444-1448
+  if (vkgsb_set_lines(impl_->renderer_, static_cast<uint32_t>(pos.size() / 6), pos.data(), col.data(), model) != VKGSB_OK)
+    throw std::runtime_error(std::string("vkgs::Engine: ") + vkgsb_last_error());
+}
+
 void Engine::WaitForLoad() {
   if (vkgsb_wait_load(impl_->renderer_) != VKGSB_OK)
     throw std::runtime_error(std::string("vkgs::Engine: ") + vkgsb_last_error());
