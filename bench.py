@@ -59,7 +59,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                          str(self.index), "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          str(self.index), "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
