@@ -180,5 +180,15 @@ def render(scene: Scene, cam: Camera, mode: int = 0, tile: int = 16):
                            ms_raster=st.ms_raster))
 
 
+def use_all_cores() -> int:
+    """OpenMP threads = the cores this process may run on (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().vko_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 def num_threads() -> int:
     return int(lib().vko_num_threads())

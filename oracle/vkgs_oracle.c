@@ -686,6 +686,15 @@ VKO_API void vko_render(uint32_t n, const float* pos, const float* cov, const fl
   if (st) { st->visible = v; st->ms_cull = t1 - t0; st->ms_sort = t2 - t1; st->ms_project = t3 - t2; st->ms_raster = t4 - t3; }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm asks for the host's cores explicitly */
+VKO_API void vko_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 VKO_API int vko_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
