@@ -34,7 +34,7 @@ N_SPLATS = 6_131_954
 N_VIEWS = 64                      # orbit the steps cycle through
 ORBIT = dict(r=1.5, phi_deg=70.0)  # ~2 M visible of 6.1 M: the reference's "view 2" regime (DETAILS.md:72)
 E2E_BATCH = 8                     # views per vkgsb_draw_batch call in the end-to-end leg
-PARAM_BYTES = 532                 # sizeof(FrameParams): the per-frame host->device upload (a kernel argument)
+PARAM_BYTES = 548                 # sizeof(FrameParams): the per-frame host->device upload (a kernel argument)
 WORKLOAD = ("C2 bicycle-shaped 6,131,954 splats SH3, 1600x900, 64-view orbit r=1.5 phi=70deg "
             "(~2 M visible, the reference's 'view 2' regime)")
 KERNELS_PER_FRAME = 9             # set_params, project, 3 depth onesweep passes, bin count / scan / place, blend

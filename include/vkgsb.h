@@ -94,10 +94,15 @@ enum vkgsb_option {
   VKGSB_OPT_STAGE_TIMING = 0, /* 1: launch stages eagerly with CUDA events between them; 0: one CUDA graph per frame */
   VKGSB_OPT_BLEND_MODE = 1,   /* vkgsb_blend_mode */
   VKGSB_OPT_PIXEL_FORMAT = 2, /* vkgsb_pixel_format */
-  VKGSB_OPT_BAND_Y0 = 3,      /* restrict binning + blending to image rows [y0,y1) (tile-band sharding) */
+  VKGSB_OPT_BAND_Y0 = 3,      /* render image rows [y0,y1) only (tile-band sharding): the rows of the band are
+                                 bit-identical to the same rows of the full frame */
   VKGSB_OPT_BAND_Y1 = 4,      /* 0 => full height */
-  VKGSB_OPT_KEEP_INSTANCES = 5 /* 1: also store the reference-format instance records (projection.comp:177-179) so
+  VKGSB_OPT_KEEP_INSTANCES = 5, /* 1: also store the reference-format instance records (projection.comp:177-179) so
                                   vkgsb_read_instances can return them; off by default (48 B/visible splat of writes) */
+  VKGSB_OPT_BAND_CULL = 6     /* default 1: while a band is set, splats whose footprint provably cannot reach it are
+                                 dropped at the cull, so sort, projection and binning shrink with the band; the visible
+                                 count and the parity taps then describe the band's subset (same relative order).
+                                 0: cull on the centre alone, as the full frame does (rank.comp:37) */
 };
 
 VKGSB_API const char* vkgsb_last_error(void);

@@ -110,3 +110,18 @@ def test_c5_shaped_large_scene_in_bands():
         _check_order_against_oracle(r, P, V, keys, ids)
         assert np.array_equal(r.draw(), img)
         _bands_equal_full(r, img, h)                                       # the 8-GPU screen-band partition of SURVEY 8(e)
+        # a band only culls, sorts and projects what can reach it (VKGSB_OPT_BAND_CULL): a conservative superset of the
+        # splats whose box touches the band, in the full frame's relative order
+        full_ids = ids
+        r.set_band(3 * h // 8, 4 * h // 8)
+        band_img = r.draw().copy()
+        vb = r.stats()["visible_point_count"]
+        bkeys, bids = r.read_sorted()
+        assert 0 < vb < st["visible_point_count"] // 2, (vb, st["visible_point_count"])
+        pos_in_full = np.full(n, -1, np.int64); pos_in_full[full_ids] = np.arange(len(full_ids))
+        assert np.all(pos_in_full[bids] >= 0) and np.all(np.diff(pos_in_full[bids]) > 0)   # subsequence of the full order
+        r.set_option(vkgs_b200.OPT_BAND_CULL, 0)
+        assert np.array_equal(r.draw(), band_img)                          # same pixels with the centre-only cull ...
+        assert r.stats()["visible_point_count"] == st["visible_point_count"]   # ... which keeps the whole visible set
+        r.set_option(vkgs_b200.OPT_BAND_CULL, 1)
+        r.set_band(0, 0)

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("VKGSB_LIB") or os.path.join(_HERE, "lib", "libvkgsb.s
 OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_CAPACITY, ERR_NO_SCENE, ERR_CANCELLED = range(7)
 BLEND_FP32, BLEND_UNORM8 = 0, 1
 FORMAT_RGBA8, FORMAT_BGRA8 = 0, 1
-OPT_STAGE_TIMING, OPT_BLEND_MODE, OPT_PIXEL_FORMAT, OPT_BAND_Y0, OPT_BAND_Y1, OPT_KEEP_INSTANCES = range(6)
+OPT_STAGE_TIMING, OPT_BLEND_MODE, OPT_PIXEL_FORMAT, OPT_BAND_Y0, OPT_BAND_Y1, OPT_KEEP_INSTANCES, OPT_BAND_CULL = range(7)
 
 
 class Config(C.Structure):

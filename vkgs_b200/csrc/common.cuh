@@ -15,6 +15,7 @@ constexpr int kTile = 16;              // origin granularity of the pinned fragm
 // (4 pixels per lane).
 constexpr int kBinW = 64, kBinH = 64, kSubW = 16, kSubH = 8;
 constexpr uint32_t kFlagKeepInstances = 1u;  // also write the reference-format instance records (parity tap)
+constexpr uint32_t kFlagBandCull = 4u;       // band rendering: k_project drops splats whose footprint cannot reach the band
 constexpr uint32_t kFlagDepthLayer = 2u;     // an opaque line layer is drawn under the splats (lines.cu): k_project also
                                              // writes ndc.z per slot, the blend stage depth-tests against the layer
 constexpr int kSubCols = kBinW / kSubW, kSubRows = kBinH / kSubH;  // 4 x 8 = 32 sub-tiles
@@ -38,6 +39,7 @@ struct Scene {
   const float* x;
   const float* y;
   const float* z;
+  const float* tr;  // largest eigenvalue of the 3-D covariance (max scale^2): only the band cull reads it
   const SplatPayload* payload;
   uint32_t n;
 };
@@ -66,6 +68,10 @@ struct FrameParams {
   uint32_t ncbins;              // coarse bins covering the band: cbins_x * rows (<= kMaxCoarseBins)
   uint32_t pad1[3];
   float pvm_lines[16];          // (proj*view)*model of the line layer (color.vert, engine.cc:1444-1448)
+  // band cull (kFlagBandCull): the footprint's pixel half-height ey satisfies
+  //   ey^2 <= bc_a * (bc_p + x_ndc^2 + y_ndc^2) * lambda_max(Sigma) / w^2 + bc_b
+  float bc_a, bc_b, bc_p;
+  float pad3;
 };
 
 // ---- control block: everything the host zeroes with one memset per frame --------------------------------------

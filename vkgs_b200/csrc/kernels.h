@@ -14,6 +14,7 @@ struct SceneStorage {
   float* x;
   float* y;
   float* z;
+  float* tr;  // largest eigenvalue of the 3-D covariance
   SplatPayload* payload;
 };
 // rows: `count` PLY vertices already on the device; offsets: 60-entry table on the device.  Writes splats

@@ -55,6 +55,8 @@ k_activate(const float* __restrict__ rows, const uint32_t* __restrict__ offsets,
   dst.x[id] = p[off[0]];
   dst.y[id] = p[off[1]];
   dst.z[id] = p[off[2]];
+  // the largest eigenvalue of Sigma = R diag(s^2) R^T: bounds every projected extent (band cull, project.cu)
+  dst.tr[id] = fmaxf(fmaxf(s0 * s0, s1 * s1), s2 * s2);
 
   uint4 line[8];
   line[0] = make_uint4(__float_as_uint(c3[0]), __float_as_uint(c3[3]), __float_as_uint(c3[6]), __float_as_uint(c3[4]));

@@ -96,6 +96,7 @@ struct vkgsb_renderer {
   int blend_mode = VKGSB_BLEND_FP32, pixel_format = VKGSB_FORMAT_RGBA8, stage_timing = 0, keep_instances = 0;
   bool last_frame_has_instances = false;
   uint32_t band_y0 = 0, band_y1 = 0;
+  int band_cull = 1;  // VKGSB_OPT_BAND_CULL
   FrameParams h_fp{};
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_valid = false;
@@ -287,12 +288,48 @@ void fill_params(vkgsb_renderer* r) {
   }
   p.ncbins = p.cbins_x * crows;
   p.pad1[0] = p.pad1[1] = p.pad1[2] = 0u;
+  // Band rendering (one GPU of a screen-band partition): splats whose footprint cannot reach the band
+  // are dropped at the cull, so sort / projection / binning shrink with the band.  The footprint's pixel box has
+  // half-height ey = 3 * (H/2) * (|RS10| + |RS11|) <= 3 * (H/2) * sqrt(trace(cov2d))   (RS RS^T = cov2d), and
+  //   trace(cov2d) = trace(K Sigma K^T) + lpx + lpy <= |K|_F^2 * lambda_max(Sigma) + lpx + lpy,
+  //   |K|_F <= |mat2(proj) J|_F * |W|_2,   |mat2(proj) J|_F^2 = (P00^2 + P11^2 + x_ndc^2 + y_ndc^2) / w^2   (w = -z_view).
+  // Valid for a projection of the reference's shape (camera.cc:25-35: diagonal 2x2 block, w = -z); any other
+  // projection matrix keeps the whole visible set.
+  {
+    const float* P = p.proj;
+    const bool shaped = P[1] == 0.f && P[2] == 0.f && P[3] == 0.f && P[4] == 0.f && P[6] == 0.f && P[7] == 0.f &&
+                        P[8] == 0.f && P[9] == 0.f && P[11] == -1.f && P[12] == 0.f && P[13] == 0.f && P[15] == 0.f;
+    const bool banded = p.band_y0 > 0u || p.band_y1 < p.height;
+    // |W|_2^2 = largest eigenvalue of W^T W (power iteration in double; never above the Frobenius bound), + 1 %
+    double G[9], v[3] = {1.0, 1.0, 1.0}, wf2 = 0.0, lam = 0.0;
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        G[a * 3 + b] = 0.0;
+        for (int k = 0; k < 3; ++k) G[a * 3 + b] += static_cast<double>(p.w3[a * 3 + k]) * p.w3[b * 3 + k];
+      }
+    for (int i = 0; i < 9; ++i) wf2 += static_cast<double>(p.w3[i]) * p.w3[i];
+    for (int it = 0; it < 64; ++it) {
+      double u[3];
+      for (int a = 0; a < 3; ++a) u[a] = G[a * 3 + 0] * v[0] + G[a * 3 + 1] * v[1] + G[a * 3 + 2] * v[2];
+      lam = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+      if (!(lam > 0.0)) break;
+      for (int a = 0; a < 3; ++a) v[a] = u[a] / lam;
+    }
+    double w2 = std::min(wf2, lam * 1.01);
+    if (!(w2 > 0.0) || !(lam > 0.0)) w2 = wf2;  // degenerate or non-finite model: the Frobenius bound, or NaN (keeps everything)
+    const float hh = 0.5f * fh;
+    p.bc_a = static_cast<float>(9.0 * hh * hh * w2);
+    p.bc_b = 9.f * hh * hh * (p.lpx + p.lpy);
+    p.bc_p = P[0] * P[0] + P[5] * P[5];
+    p.pad3 = 0.f;
+    if (shaped && banded && r->band_cull) p.flags |= kFlagBandCull;
+  }
 }
 
 // Stage kernels of one frame on `s`.  With `timed`, CUDA events bracket the stages (ev[0..4]).
 int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   const uint32_t n = r->scene_n.load();
-  Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.payload, n};
+  Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, n};
   CU_TRY(cudaMemsetAsync(r->zero_region, 0, r->zero_bytes, s));
   // look-back words of the depth sort: only partitions of the <= n visible splats can be touched
   CU_TRY(cudaMemsetAsync(r->lookback_depth, 0, sort_lookback_bytes(n), s));
@@ -423,7 +460,7 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
     if ((e = cudaEventCreateWithFlags(&r->copy_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
   }
   const size_t N = r->max_splats, P = r->max_pairs;
-  ALLOC(r->scene.x, N * 4); ALLOC(r->scene.y, N * 4); ALLOC(r->scene.z, N * 4);
+  ALLOC(r->scene.x, N * 4); ALLOC(r->scene.y, N * 4); ALLOC(r->scene.z, N * 4); ALLOC(r->scene.tr, N * 4);
   ALLOC(r->scene.payload, N * sizeof(SplatPayload));
   ALLOC(r->keys, N * 4); ALLOC(r->slots, N * 4); ALLOC(r->keys_alt, N * 4); ALLOC(r->slots_alt, N * 4);
   ALLOC(r->vis_id, N * 4);
@@ -477,7 +514,7 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   if (r->stream) cudaStreamSynchronize(r->stream);
   if (r->load_stream) cudaStreamSynchronize(r->load_stream);
   if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
-  void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
+  void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
                  r->vis_id, r->inst, r->rrec, r->bin_rect, r->bin_slots, r->bin.tile_pairs, r->bin.tile_item, r->bin.tile_bin, r->bin.bin_total,
                  r->lookback_depth, r->zero_region, r->d_fp, r->image, r->stage[0], r->stage[1], r->d_offsets, r->d_rows[0],
                  r->d_rows[1], r->line_pos, r->line_col, r->zndc, r->layer};
@@ -516,6 +553,7 @@ int vkgsb_set_option(vkgsb_renderer* r, int option, int64_t value) {
     case VKGSB_OPT_KEEP_INSTANCES: r->keep_instances = value != 0; break;
     case VKGSB_OPT_BAND_Y0: r->band_y0 = static_cast<uint32_t>(value); break;
     case VKGSB_OPT_BAND_Y1: r->band_y1 = static_cast<uint32_t>(value); break;
+    case VKGSB_OPT_BAND_CULL: r->band_cull = value != 0; break;
     default: return fail(VKGSB_ERR_INVALID, "unknown option");
   }
   invalidate_graph(r);
