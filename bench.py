@@ -47,12 +47,16 @@ def view_camera(i):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe).  nvidia-smi takes a few
+    hundred ms to deliver its first line and the timed region is shorter than that, so the sampler is started before the
+    warm-up, start() returns once the first sample is in, and stop() keeps the samples stamped inside
+    [mark_begin(), mark_end()] (the nearest ones around it when the region fell between two samples)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.path = index, None, None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -60,36 +64,64 @@ class ClockSampler:
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                           str(self.index), "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
+            deadline = time.time() + 3.0
+            while time.time() < deadline and os.path.getsize(self.path) == 0:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _epoch(stamp):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
+        time.sleep(0.05)  # one more sample behind the region
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 p = [x.strip() for x in line.split(",")]
-                if len(p) < 9:
+                if len(p) < 10:
                     continue
                 try:
-                    sm.append(float(p[1])); mx.append(float(p[2]))
+                    rows.append((self._epoch(p[0]), float(p[2]), float(p[3]), p[6:10]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out["sm_mhz"] = float(np.median(sm)); out["sm_max_mhz"] = float(max(mx)); out["samples"] = len(sm)
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        if not inside and rows and self.t0 is not None:   # the region fell between two 20 ms samples: its neighbours
+            mid = 0.5 * (self.t0 + self.t1)
+            inside = sorted((r for r in rows if r[0] is not None), key=lambda r: abs(r[0] - mid))[:2]
+        if not inside:
+            inside = rows
+        reasons = set()
+        for _, _, _, flags in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if inside:
+            out["sm_mhz"] = float(np.median([r[1] for r in inside]))
+            out["sm_max_mhz"] = float(max(r[2] for r in inside))
+            out["samples"] = len(inside)
         out["reasons"] = sorted(reasons)
         return out
 
@@ -261,14 +293,19 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    for i in range(W):   # the GPU stays under load while the sampler comes up
+        frame_device(i)
+    drain()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record(stream)
     for i in range(K):
         frame_device(i)
     drain()   # every gathered image has arrived on rank 0 inside the timed region
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = vdist.max_over_ranks(e0.elapsed_time(e1), dev)
     clocks = sampler.stop()
     st = r.stats()
