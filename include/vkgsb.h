@@ -141,6 +141,10 @@ VKGSB_API int vkgsb_set_viewport(vkgsb_renderer* r, uint32_t width, uint32_t hei
 VKGSB_API int vkgsb_set_lines(vkgsb_renderer* r, uint32_t n_lines, const float* positions, const float* colors,
                               const float model[16]);
 
+/* Splat centres per image row of the LAST frame drawn (rows[height], host memory): the load a screen-band partition
+ * balances its band edges on (vkgs_b200.dist.balanced_band_edges).  No counterpart in the reference. */
+VKGSB_API int vkgsb_row_histogram(vkgsb_renderer* r, uint32_t* rows, uint32_t capacity);
+
 /* One frame: rank -> sort -> projection -> draw (engine.cc:1164-1290), into an RGBA8/BGRA8 image of
  * width*height*4 bytes.  dst may be NULL (image stays in the renderer, see vkgsb_image_device_ptr), a host pointer
  * (dst_is_device = 0: device->host copy, returns when the pixels are in dst) or a device pointer (dst_is_device = 1:

@@ -108,3 +108,20 @@ def test_two_gloo_ranks_reproduce_the_single_process_result(tmp_path):
     assert np.array_equal(z["frame"], want[1]), "bands do not concatenate to the full frame"
     assert float(z["slowest"]) == 2.0  # max over ranks, the timing rule of bench.py
     assert list(z["edges"]) == vdist.band_edges(H, 2)
+
+
+def test_balanced_band_edges_cover_the_frame_and_even_out_the_load():
+    rng = np.random.default_rng(3)
+    h = 900
+    load = rng.integers(0, 50, h).astype(np.float64)
+    load[380:520] += 4000            # the scene sits in the middle rows
+    for world in (1, 2, 4, 8):
+        e = vdist.balanced_band_edges(load, world)
+        assert e[0] == 0 and e[-1] == h and len(e) == world + 1
+        assert all(b - a >= 8 for a, b in zip(e[:-1], e[1:]))
+        per = [load[a:b].sum() for a, b in zip(e[:-1], e[1:])]
+        equal = [load[a:b].sum() for a, b in zip(vdist.band_edges(h, world)[:-1], vdist.band_edges(h, world)[1:])]
+        assert max(per) <= max(equal) + 1e-9
+        if world == 8:
+            assert max(per) < 0.25 * load.sum() < max(equal)      # equal-height bands leave most of it to two ranks
+    assert vdist.balanced_band_edges(np.zeros(64), 4) == [0, 16, 32, 48, 64]

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--splats", dest="n", type=int, default=50_000_000)
     ap.add_argument("--frames", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--equal", action="store_true", help="equal-height bands instead of load-balanced ones")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -45,21 +46,37 @@ def main():
     for i in range(8):
         c = pycam.orbit(w, h, r=6.0, phi_deg=70.0, theta_deg=30.0 + 45.0 * i)
         cams.append(vkgs_b200.camera_block(c.projection_matrix(), c.view_matrix(), c.eye()))
-    edges = vdist.band_edges(h, world) if hasattr(vdist, "band_edges") else [int(round(h * g / world)) for g in range(world + 1)]
+    ap_balanced = "--equal" not in sys.argv
+    if world > 1 and ap_balanced:
+        # band edges balanced on the splat centres per row, summed over one whole frame per view of the orbit (every rank
+        # holds the scene and computes the same edges).  One set of edges for the whole run: a band is part of the
+        # recorded frame graph, changing it every frame would re-record the graph every frame.
+        hist = np.zeros(h, np.float64)
+        for cam in cams:
+            r.set_camera(block=cam)
+            r.draw_device()
+            r.sync()
+            hist += r.row_histogram()
+        edges = vdist.balanced_band_edges(hist, world)
+    else:
+        edges = vdist.band_edges(h, world)
+    edges_per_view = [edges] * len(cams)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     frame = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
     gathered = [torch.empty_like(frame) for _ in range(world)] if (world > 1 and rank == 0) else None
 
-    def run(n_frames, band):
-        r.set_band(*band)
+    def run(n_frames, banded):
         for i in range(n_frames):
+            e = edges_per_view[i % len(cams)]
+            band = (e[rank], e[rank + 1]) if banded else (0, 0)
+            r.set_band(*band)
             r.set_camera(block=cams[i % len(cams)])
             r.draw_device(dst_ptr=frame.data_ptr(), stream=stream.cuda_stream)
-            if world > 1 and band != (0, 0):
+            if world > 1 and banded:
                 dist.gather(frame, gathered, dst=0)   # every rank's rows; rank 0 keeps rows [edges[g], edges[g+1]) of each
 
-    band = (edges[rank], edges[rank + 1]) if world > 1 else (0, 0)
+    band = world > 1
     run(args.warmup, band)
     torch.cuda.synchronize()
     if world > 1:
@@ -90,6 +107,8 @@ def main():
         torch.cuda.synchronize()
         whole = e0.elapsed_time(e1) / 8
         print(json.dumps({"config": f"C5 {args.n:,} splats, 1600x900, {world} band(s) on {world} GPU(s), bands gathered to rank 0 (NCCL)",
+                          "band_edges": "balanced on the per-row splat histogram" if ap_balanced else "equal heights",
+                          "edges_view0": edges_per_view[0],
                           "ms_per_frame": round(ms, 4), "fps": round(1e3 / ms, 1), "slowest_band_stages_ms_total": round(stage_total, 4),
                           "rank0_band": {k: round(st[k], 4) for k in ("ms_project", "ms_sort", "ms_bin", "ms_blend", "ms_total")},
                           "rank0_band_visible": st["visible_point_count"],

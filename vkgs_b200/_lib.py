@@ -55,6 +55,7 @@ SIGNATURES = {
     "vkgsb_image_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
     "vkgsb_sync": (C.c_int, [_P]),
     "vkgsb_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "vkgsb_row_histogram": (C.c_int, [_P, _P, C.c_uint32]),
     "vkgsb_read_sorted": (C.c_int, [_P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "vkgsb_read_instances": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "vkgsb_read_scene": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),

@@ -452,6 +452,28 @@ void launch_bin(const FrameParams* d_fp, uint32_t ncbins, Control* d_ctrl, const
                                                  d_bin_slots);
 }
 
+// Splat centres per image row of the last frame (from the raster records): what a screen-band partition balances on.
+__global__ void __launch_bounds__(256)
+k_row_histogram(const Control* __restrict__ ctrl, const float4* __restrict__ rrec, uint32_t height,
+                uint32_t* __restrict__ hist) {
+  const uint32_t V = ctrl->visible_count;
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < V; i += gridDim.x * 256) {
+    const float cpy = rrec[i * 3 + 1].y;  // pixel-frame centre row (project.cu: raster_record)
+    if (cpy == cpy) {
+      const float r = fminf(fmaxf(rintf(cpy), 0.f), static_cast<float>(height - 1));
+      atomicAdd(&hist[static_cast<uint32_t>(r)], 1u);
+    }
+  }
+}
+
+void launch_row_histogram(const Control* d_ctrl, const float* d_rrec, uint32_t max_visible, uint32_t height,
+                          uint32_t* d_hist, cudaStream_t stream) {
+  cudaMemsetAsync(d_hist, 0, height * sizeof(uint32_t), stream);
+  uint32_t want = (max_visible + 255) / 256;
+  int blocks = static_cast<int>(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+  k_row_histogram<<<blocks, 256, 0, stream>>>(d_ctrl, reinterpret_cast<const float4*>(d_rrec), height, d_hist);
+}
+
 void launch_gather_sorted(const Control* d_ctrl, const uint32_t* d_sorted_slots, const uint32_t* d_vis_id,
                           const float* d_inst, uint32_t max_visible, uint32_t* d_ids_out, float* d_inst_out,
                           cudaStream_t stream) {

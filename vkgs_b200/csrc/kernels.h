@@ -87,6 +87,8 @@ void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2*
                   uint8_t* d_image, cudaStream_t stream);
 
 // ---- misc ----------------------------------------------------------------------------------------------------------
+void launch_row_histogram(const Control* d_ctrl, const float* d_rrec, uint32_t max_visible, uint32_t height,
+                          uint32_t* d_hist, cudaStream_t stream);
 void launch_gather_sorted(const Control* d_ctrl, const uint32_t* d_sorted_slots, const uint32_t* d_vis_id,
                           const float* d_inst, uint32_t max_visible, uint32_t* d_ids_out, float* d_inst_out,
                           cudaStream_t stream);

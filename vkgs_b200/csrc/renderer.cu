@@ -782,6 +782,22 @@ int vkgsb_read_sorted(vkgsb_renderer* r, uint32_t* keys, uint32_t* ids, uint32_t
   return VKGSB_OK;
 }
 
+int vkgsb_row_histogram(vkgsb_renderer* r, uint32_t* rows, uint32_t capacity) {
+  if (!r || !rows) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (r->height == 0 || capacity < r->height) return fail(VKGSB_ERR_CAPACITY, "rows[] is shorter than the viewport height");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  std::lock_guard<std::mutex> g(r->draw_mutex);
+  CU_TRY(cudaDeviceSynchronize());
+  uint32_t* d_hist = nullptr;
+  CU_TRY(cudaMalloc(&d_hist, r->height * sizeof(uint32_t)));
+  launch_row_histogram(r->ctrl, r->rrec, r->scene_n.load(), r->height, d_hist, r->stream);
+  cudaError_t e = cudaStreamSynchronize(r->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(rows, d_hist, r->height * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  cudaFree(d_hist);
+  CU_TRY(e);
+  return VKGSB_OK;
+}
+
 int vkgsb_read_instances(vkgsb_renderer* r, float* inst, uint32_t capacity, uint32_t* count) {
   if (!r || !count) return fail(VKGSB_ERR_INVALID, "null argument");
   if (set_device(r)) return VKGSB_ERR_CUDA;

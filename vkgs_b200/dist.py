@@ -29,6 +29,25 @@ def band_edges(height: int, world: int, align: int = 16) -> List[int]:
     return edges
 
 
+def balanced_band_edges(row_load, world: int, min_rows: int = 8) -> List[int]:
+    """Row boundaries of `world` bands carrying about equal load: `row_load[y]` = splat centres on image row y of a
+    previous frame (Renderer.row_histogram()).  A constant per row is added for the per-pixel cost of an empty band,
+    every band keeps at least `min_rows` rows, the bands cover [0, height)."""
+    import numpy as np
+    load = np.asarray(row_load, np.float64)
+    h = len(load)
+    load = load + max(load.sum(), 1.0) / h * 0.05
+    cum = np.concatenate([[0.0], np.cumsum(load)])
+    edges = [0]
+    for g in range(1, world):
+        y = int(np.searchsorted(cum, cum[-1] * g / world))
+        y = max(y, edges[-1] + min_rows)
+        y = min(y, h - (world - g) * min_rows)
+        edges.append(y)
+    edges.append(h)
+    return edges
+
+
 def gather_images(local, dst: int = 0, group=None):
     """Gather equally shaped uint8 image tensors [B,H,W,4] to rank `dst`.  Returns the list on dst, else None."""
     import torch.distributed as dist

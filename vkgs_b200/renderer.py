@@ -166,6 +166,12 @@ class Renderer:
         L.check(L.lib().vkgsb_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in L.Stats._fields_}
 
+    def row_histogram(self) -> np.ndarray:
+        """Splat centres per image row of the last frame (what balanced band edges are computed from)."""
+        rows = np.zeros(self.height, np.uint32)
+        L.check(L.lib().vkgsb_row_histogram(self._h, _ptr(rows), self.height))
+        return rows
+
     # ---- parity taps
     def read_sorted(self):
         cnt = C.c_uint32()
