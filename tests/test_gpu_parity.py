@@ -343,3 +343,20 @@ def test_instances_tap_needs_the_option(c1):
         assert r.read_instances().shape[1] == 12
         r.set_option(vkgs_b200.OPT_KEEP_INSTANCES, 0)
         assert np.array_equal(r.draw(), a)                               # the tap does not change the image
+
+
+def test_row_histogram_counts_the_centres_of_the_last_frame(small_renderer, c1):
+    """vkgsb_row_histogram (the load screen-band partitions balance on) against the instance records of the same frame."""
+    rows, P, V, E = c1
+    r = small_renderer
+    r.upload_splats(rows)
+    r.set_viewport(800, 600)
+    r.set_blend_mode(vkgs_b200.BLEND_FP32)
+    r.set_camera(P, V, E)
+    r.draw()
+    hist = r.row_histogram()
+    inst = r.read_instances()
+    cpy = np.float32(300.0) * inst[:, 1] + np.float32(299.5)          # fma(ndc.y, H/2, H/2 - 1/2) up to one rounding
+    want = np.bincount(np.clip(np.rint(cpy[~np.isnan(cpy)]), 0, 599).astype(np.int64), minlength=600)
+    assert hist.shape == (600,) and hist.sum() == (~np.isnan(cpy)).sum() == r.stats()["visible_point_count"]
+    assert np.abs(hist.astype(np.int64) - want).sum() <= 4            # a centre exactly between two rows may round either way
