@@ -73,9 +73,10 @@ __global__ void __launch_bounds__(256) k_sort_hist(SortArgs a) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + tid; i < used; i += static_cast<size_t>(gridDim.x) * 256)
     a.lookback[i] = 0u;
 
-  // Depth keys and tile ids are heavily clustered in their upper digits (a handful of exponent values; runs of
-  // neighbouring tiles), so lanes are aggregated with match.any first: one shared-memory atomic per distinct digit
-  // per warp instead of a 32-way same-address conflict.
+  // One shared-memory atomic per key and digit - except where a whole warp holds the same digit (the upper digits of
+  // depth keys: a handful of exponent values), which would be a 32-way same-address pile-up: one vote finds that case
+  // and a single lane adds the warp's count.  (Aggregating every digit with match.any cost a round per distinct value -
+  // ~30 for a dense digit - and made this kernel a third of the whole sort on uniform keys.)
   const uint32_t n4 = n / 4;
   const uint4* k4 = reinterpret_cast<const uint4*>(a.keys);
   const uint32_t lane = tid & 31u;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256) k_sort_hist(SortArgs a) {
     const uint32_t ks[4] = {k.x, k.y, k.z, k.w};
     const uint32_t active = __ballot_sync(0xffffffffu, ok);
     if (!ok) continue;
+    const uint32_t leader = __ffs(active) - 1;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int sh = a.begin_bit;
@@ -93,8 +95,12 @@ __global__ void __launch_bounds__(256) k_sort_hist(SortArgs a) {
       for (int p = 0; p < a.npass; ++p) {
         const int bits = pass_bits(a, p);
         const uint32_t d = (ks[j] >> sh) & ((1u << bits) - 1u);
-        const uint32_t peers = __match_any_sync(active, d);
-        if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[b0 + d], __popc(peers));
+        const uint32_t d0 = __shfl_sync(active, d, leader);
+        if (__all_sync(active, d == d0)) {
+          if (lane == leader) atomicAdd(&s_hist[b0 + d], __popc(active));
+        } else {
+          atomicAdd(&s_hist[b0 + d], 1u);
+        }
         sh += bits;
         b0 += 1u << bits;
       }
