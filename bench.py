@@ -335,7 +335,7 @@ def main():
     # ---- per-stage times (eager launches with events between stages)
     r.set_option(L.OPT_STAGE_TIMING, 1)
     acc = dict(ms_project=0.0, ms_sort=0.0, ms_bin=0.0, ms_blend=0.0, ms_total=0.0)
-    vis, pairs = [], []
+    vis, pairs, totals = [], [], []
     for i in range(W + K):
         r.set_camera(block=cams[i % len(cams)])
         r.draw_device(stream=sptr)
@@ -343,7 +343,7 @@ def main():
             s = r.stats()
             for k in acc:
                 acc[k] += s[k]
-            vis.append(s["visible_point_count"]); pairs.append(s["pair_count"])
+            vis.append(s["visible_point_count"]); pairs.append(s["pair_count"]); totals.append(s["ms_total"])
     r.set_option(L.OPT_STAGE_TIMING, 0)
     stage = {k: v / K for k, v in acc.items()}
     V_mean, D_mean = float(np.mean(vis)), float(np.mean(pairs))
@@ -370,6 +370,9 @@ def main():
                        "pair_overflow": int(st["pair_overflow"])},
             "stages_ms": {"project": stage["ms_project"], "sort": stage["ms_sort"], "bin": stage["ms_bin"],
                           "blend": stage["ms_blend"], "total": stage["ms_total"]},
+            # per-frame device time over the orbit (the views differ in cost): SURVEY.md 8(d) asks for the spread
+            "frame_ms": {"p10": float(np.percentile(totals, 10)), "p50": float(np.percentile(totals, 50)),
+                         "p90": float(np.percentile(totals, 90))},
             "sort_gkeys_per_s": sort_gkeys,
             "sort_hbm_frac": 68.0 * V_mean / (stage["ms_sort"] * 1e-3) / 1e9 / hbm_peak,
             "roofline": {"kernel": "k_project", "bound": "hbm", "achieved": proj_gbs, "peak": hbm_peak, "unit": "GB/s",
