@@ -849,7 +849,8 @@ int vkgsb_read_scene(vkgsb_renderer* r, float* pos, float* cov, float* opacity, 
 }
 
 // ---- stage-level sort plug-in (vrdx* surface) -----------------------------------------------------------------------
-// storage layout: [hist 4x256 u32][tickets 4 u32 (+pad)][look-back 4 x parts x 256 u32][keys_alt max_n][vals_alt max_n]
+// storage layout: [hist 4x256 u32][tickets 4 u32 (+pad)][tree of partition aggregates + arrival counters,
+// sort_lookback_bytes(max_n)][keys_alt max_n][vals_alt max_n]
 static size_t sort_storage_layout(uint32_t max_n, size_t* off_lookback, size_t* off_keys, size_t* off_vals) {
   size_t o = 4 * 256 * 4 + 64;
   *off_lookback = o;
