@@ -47,6 +47,16 @@ def _render_band(scene, i, y0, y1):
     return img
 
 
+def _row_histogram(scene, i):
+    """What vkgsb_row_histogram returns on the GPU: visible splat centres per image row."""
+    P, V, E = _camera(i)
+    keys, ids = O.cull(scene, O.compose_pvm(P, V))
+    inst = O.project(scene, ids, O.make_camera(P, V, E, W, H), 0)
+    cpy = np.float32(H / 2) * inst[:, 1] + np.float32(H / 2 - 0.5)
+    cpy = cpy[~np.isnan(cpy)]
+    return np.bincount(np.clip(np.rint(cpy), 0, H - 1).astype(np.int64), minlength=H)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -69,13 +79,20 @@ def _worker(rank, world, port, out_path):
         edges = vdist.band_edges(H, world)
         band = torch.from_numpy(_render_band(scene, 1, edges[rank], edges[rank + 1]))[None]
         got_b = vdist.gather_images(band, dst=0)
+        # ---- by load-balanced band: edges from the per-row histogram of splat centres (every rank computes the same)
+        load = _row_histogram(scene, 1).astype(np.float64)
+        load[: H // 3] *= 6.0   # as if the upper third were the expensive part: the edge moves off the tile grid
+        bal = vdist.balanced_band_edges(load, world, min_rows=4)
+        band2 = torch.from_numpy(_render_band(scene, 1, bal[rank], bal[rank + 1]))[None]
+        got_c = vdist.gather_images(band2, dst=0)
         slowest = vdist.max_over_ranks(float(rank + 1))
         if rank == 0:
             views = vdist.assemble_views(got, N_VIEWS).numpy()
             frame = vdist.assemble_bands(got_b, edges).numpy()[0]
-            np.savez(out_path, views=views, frame=frame, slowest=slowest, edges=np.array(edges))
+            frame2 = vdist.assemble_bands(got_c, bal).numpy()[0]
+            np.savez(out_path, views=views, frame=frame, frame2=frame2, slowest=slowest, edges=np.array(edges), bal=np.array(bal))
         else:
-            assert got is None and got_b is None
+            assert got is None and got_b is None and got_c is None
     finally:
         dist.destroy_process_group()
 
@@ -108,6 +125,9 @@ def test_two_gloo_ranks_reproduce_the_single_process_result(tmp_path):
     assert np.array_equal(z["frame"], want[1]), "bands do not concatenate to the full frame"
     assert float(z["slowest"]) == 2.0  # max over ranks, the timing rule of bench.py
     assert list(z["edges"]) == vdist.band_edges(H, 2)
+    assert np.array_equal(z["frame2"], want[1]), "load-balanced bands do not concatenate to the full frame"
+    bal = list(z["bal"])
+    assert bal[0] == 0 and bal[-1] == H and bal != vdist.band_edges(H, 2)
 
 
 def test_balanced_band_edges_cover_the_frame_and_even_out_the_load():
