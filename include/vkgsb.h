@@ -88,6 +88,9 @@ typedef struct vkgsb_stats {
   float ms_blend;               /* splat.vert/.frag + ROP equivalent */
   float ms_total;
   uint64_t frame_counter;
+  uint32_t blend_full_walks;    /* VKGSB_BLEND_UNORM8: warps (16x8 pixels) whose late-start bracket stayed open and that
+                                   walked their whole list instead (exact either way; a cost indicator) */
+  uint32_t pad0;
 } vkgsb_stats;
 
 enum vkgsb_option {

@@ -29,7 +29,8 @@ class Stats(C.Structure):
     _fields_ = [("total_point_count", C.c_uint32), ("loaded_point_count", C.c_uint32),
                 ("visible_point_count", C.c_uint32), ("pair_overflow", C.c_uint32), ("pair_count", C.c_uint64),
                 ("ms_project", C.c_float), ("ms_sort", C.c_float), ("ms_bin", C.c_float), ("ms_blend", C.c_float),
-                ("ms_total", C.c_float), ("frame_counter", C.c_uint64)]
+                ("ms_total", C.c_float), ("frame_counter", C.c_uint64), ("blend_full_walks", C.c_uint32),
+                ("pad0", C.c_uint32)]
 
 
 # every entry point include/vkgsb.h declares: name -> (restype, argtypes)

@@ -442,7 +442,7 @@ void launch_bin(const FrameParams* d_fp, uint32_t ncbins, Control* d_ctrl, const
   const uint32_t tiles = bin_num_tiles(max_visible);
   if (tiles == 0 || ncbins == 0) return;
   const uint32_t max_items = bin_max_items(max_visible, max_pairs);
-  const uint32_t items = max_items < 148u * 8u ? max_items : 148u * 8u;  // persistent: CTAs stride over the items
+  const uint32_t items = max_items < static_cast<uint32_t>(sm_count()) * 8u ? max_items : static_cast<uint32_t>(sm_count()) * 8u;  // persistent: CTAs stride over the items
   k_bin_tiles<<<tiles, kBinThreads, 0, stream>>>(d_fp, d_ctrl, d_sorted_slots, d_bin_rect, w.tile_stride, w.tile_bin,
                                                  w.tile_pairs);
   k_bin_scan<<<ncbins + 1, 1024, 0, stream>>>(d_ctrl, ncbins, max_pairs, w.tile_stride, w.tile_pairs, w.tile_bin,
@@ -470,7 +470,7 @@ void launch_row_histogram(const Control* d_ctrl, const float* d_rrec, uint32_t m
                           uint32_t* d_hist, cudaStream_t stream) {
   cudaMemsetAsync(d_hist, 0, height * sizeof(uint32_t), stream);
   uint32_t want = (max_visible + 255) / 256;
-  int blocks = static_cast<int>(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+  int blocks = static_cast<int>(want < static_cast<uint32_t>(sm_count()) * 8 ? (want ? want : 1) : static_cast<uint32_t>(sm_count()) * 8);
   k_row_histogram<<<blocks, 256, 0, stream>>>(d_ctrl, reinterpret_cast<const float4*>(d_rrec), height, d_hist);
 }
 
@@ -478,7 +478,7 @@ void launch_gather_sorted(const Control* d_ctrl, const uint32_t* d_sorted_slots,
                           const float* d_inst, uint32_t max_visible, uint32_t* d_ids_out, float* d_inst_out,
                           cudaStream_t stream) {
   uint32_t want = (max_visible + 255) / 256;
-  int blocks = static_cast<int>(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+  int blocks = static_cast<int>(want < static_cast<uint32_t>(sm_count()) * 8 ? (want ? want : 1) : static_cast<uint32_t>(sm_count()) * 8);
   k_gather_sorted<<<blocks, 256, 0, stream>>>(d_ctrl, d_sorted_slots, d_vis_id, reinterpret_cast<const float4*>(d_inst),
                                               d_ids_out, reinterpret_cast<float4*>(d_inst_out));
 }

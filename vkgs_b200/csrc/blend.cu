@@ -3,11 +3,12 @@
 // SRC_ALPHA / ONE_MINUS_SRC_ALPHA for colour AND alpha (engine.cc:281-289), clear (0,0,0,1) (engine.cc:1382-1387),
 // depth LESS / no write (graphics_pipeline.cc:79-81; applied in bin.cu), B8G8R8A8_UNORM target (render_pass.cc:15).
 //
-// One 1024-thread CTA per 64x64-pixel bin streams the nearest-first splat list of the COARSE bin it lies in (bin.cu)
-// in batches of 1024 through shared memory.  While staging, each thread turns its splat's pixel bounding box into a 32-bit mask over the bin's
-// 4x8 sub-tiles (16x8 pixels, one per warp); each warp then picks its splats out of the batch with one ballot per
-// 32 entries and shades them, 4 pixels per lane.  So a splat only costs the warps it can touch, and a warp whose 128
-// pixels are all saturated drops out of the masks; the CTA stops when every warp has.
+// One CTA of 4*ROWS warps owns a region of 64 x 8*ROWS pixels and streams the nearest-first splat list of the COARSE
+// bin it lies in (bin.cu) in batches of 1024 through shared memory.  While staging, each thread turns its splat's pixel
+// bounding box into a mask over the region's 4 x ROWS sub-tiles (16x8 pixels, one per warp); each warp then picks its
+// splats out of the batch with one ballot per 32 entries and shades them, 4 pixels per lane.  So a splat only costs the
+// warps it can touch, and a warp whose 128 pixels are all saturated drops out of the masks; the CTA stops when every
+// warp has.
 // Per-fragment arithmetic is the pinned form shared with oracle/vkgs_oracle.c (16-pixel-tile-origin-relative):
 //   px = fma(A00, lx, fma(A01, ly, bx)),  py = fma(A10, lx, fma(A11, ly, by)),  covered <=> |px|<=3 && |py|<=3
 // with A = (diag(W/2,H/2) * RS)^-1 (bin.cu) and b = A * (tile_origin - centre_px) from non-fused mul/add.
@@ -15,38 +16,62 @@
 // VKGSB_BLEND_FP32   front-to-back: C += c*a*T, A += a*a*T, T *= 1-a; a pixel retires at T < 1e-4.  In exact
 //                    arithmetic identical to the reference's back-to-front recurrence (C <- c*a + C*(1-a),
 //                    A <- a*a + A*(1-a), A0 = 1); one UNORM8 rounding at the end.
-// VKGSB_BLEND_UNORM8 back-to-front, destination re-quantised after every splat like an 8-bit ROP:
-//                    q <- rint(fma(255*src, a, q*(1-a))); no early exit possible.
+// VKGSB_BLEND_UNORM8 the reference's target semantics: back-to-front, destination re-quantised after every splat like an
+//                    8-bit ROP, q <- rint(fma(255*src, a, q*(1-a))).  The recurrence cannot stop early, but it can
+//                    START late, exactly: every step q -> rint(fma(s, a, q*(1-a))) is monotone non-decreasing in q
+//                    (a in [0,1]), so a whole run of splats F satisfies F(0) <= F(q) <= F(255) for every possible
+//                    destination value q.  A front-to-back pre-pass (transmittance only) finds per pixel the list
+//                    position where T < 1e-4; the back-to-front walk starts THERE with the bracket lo = 0, hi = 255 in
+//                    every channel and runs both ends through the same recurrence.  Where the ends meet (they do after
+//                    a few opaque splats; from then on one state is carried) the result is what the full walk over
+//                    everything behind would have produced, bit for bit, whatever that is.  A warp in which some
+//                    pixel's ends have NOT met at the front of the list repeats the walk over the entire list
+//                    (counted in Control::blend_full_walks): exact always, fast where splats are opaque.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vkgsb {
 
-constexpr int kBlendThreads = 1024;
+#ifndef VKGSB_BLEND_ROWS_FP32
+#define VKGSB_BLEND_ROWS_FP32 8
+#endif
+#ifndef VKGSB_BLEND_ROWS_UNORM8
+#define VKGSB_BLEND_ROWS_UNORM8 4
+#endif
+constexpr int kRowsFp32 = VKGSB_BLEND_ROWS_FP32;      // region = 64 x 8*ROWS pixels, 4*ROWS warps
+constexpr int kRowsUnorm8 = VKGSB_BLEND_ROWS_UNORM8;  // the bracket state needs > 64 registers: half the threads per CTA
 constexpr int kBatch = 1024;
 constexpr int kPix = 4;  // pixels per lane: rows ly0 + 2k of a 16x8 sub-tile
 constexpr float kTransmittanceCut = 1e-4f;
-constexpr size_t kBlendSmem = kBatch * (3 * sizeof(float4) + sizeof(uint32_t));
-constexpr size_t kBlendSmemLayer = kBlendSmem + kBatch * sizeof(float);  // + ndc.z of the staged entries
+constexpr uint32_t kNoCut = 0xffffffffu;
+constexpr float kRound = 12582912.f;  // 1.5 * 2^23: (x + kRound) - kRound == rintf(x) for 0 <= x < 2^22 (RNE, ties to even)
+
+constexpr size_t blend_smem(bool layer) {
+  return kBatch * (3 * sizeof(float4) + sizeof(uint32_t)) + (layer ? kBatch * sizeof(float) : 0);
+}
 
 __device__ __forceinline__ uint32_t quantize8(float x) {  // RNE, saturating
   return static_cast<uint32_t>(__float2int_rn(__saturatef(x) * 255.f));
 }
 __device__ __forceinline__ uint32_t clamp255(float q) { return static_cast<uint32_t>(fminf(fmaxf(q, 0.f), 255.f)); }
+__device__ __forceinline__ float rint255(float x) { return __fsub_rn(__fadd_rn(x, kRound), kRound); }
 
 __device__ __forceinline__ uint32_t pack_pixel(uint32_t r, uint32_t g, uint32_t b, uint32_t a, int bgra) {
   return bgra ? (b | (g << 8) | (r << 16) | (a << 24)) : (r | (g << 8) | (b << 16) | (a << 24));
 }
 
-// 32-bit mask (bit = row * 4 + col) of the bin's sub-tiles a pixel box [x0,x1] x [y0,y1] touches.
-__device__ __forceinline__ uint32_t subtile_mask(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, uint32_t bin_x,
-                                                 uint32_t bin_y) {
-  // entries come from the coarse bin's list: most boxes miss this 64x64 bin altogether (also the empty box x0 > x1)
-  if (x1 < bin_x || x0 >= bin_x + kBinW || y1 < bin_y || y0 >= bin_y + kBinH || x0 > x1 || y0 > y1) return 0u;
-  const int c0 = max(static_cast<int>(x0) - static_cast<int>(bin_x), 0) / kSubW;
-  const int c1 = min(static_cast<int>(x1) - static_cast<int>(bin_x), kBinW - 1) / kSubW;
-  const int r0 = max(static_cast<int>(y0) - static_cast<int>(bin_y), 0) / kSubH;
-  const int r1 = min(static_cast<int>(y1) - static_cast<int>(bin_y), kBinH - 1) / kSubH;
+// Mask (bit = row * 4 + col) of the region's sub-tiles a pixel box [x0,x1] x [y0,y1] touches; the region is
+// 64 x 8*ROWS pixels at (reg_x, reg_y).
+template <int ROWS>
+__device__ __forceinline__ uint32_t subtile_mask(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, uint32_t reg_x,
+                                                 uint32_t reg_y) {
+  constexpr int RW = kBinW, RH = kSubH * ROWS;
+  // entries come from the coarse bin's list: most boxes miss this region altogether (also the empty box x0 > x1)
+  if (x1 < reg_x || x0 >= reg_x + RW || y1 < reg_y || y0 >= reg_y + RH || x0 > x1 || y0 > y1) return 0u;
+  const int c0 = max(static_cast<int>(x0) - static_cast<int>(reg_x), 0) / kSubW;
+  const int c1 = min(static_cast<int>(x1) - static_cast<int>(reg_x), RW - 1) / kSubW;
+  const int r0 = max(static_cast<int>(y0) - static_cast<int>(reg_y), 0) / kSubH;
+  const int r1 = min(static_cast<int>(y1) - static_cast<int>(reg_y), RH - 1) / kSubH;
   if (c1 < c0 || r1 < r0) return 0u;
   const uint32_t cols = ((1u << (c1 - c0 + 1)) - 1u) << c0;                                       // 4 bits
   const uint32_t rows = static_cast<uint32_t>(((1ull << (4 * (r1 + 1))) - (1ull << (4 * r0)))) & 0x11111111u;
@@ -56,24 +81,25 @@ __device__ __forceinline__ uint32_t subtile_mask(uint32_t x0, uint32_t x1, uint3
 // LAYER: an opaque line layer lies under the splats (lines.cu; the reference's axis / grid, engine.cc:1440-1469).  A
 // fragment is kept only if the splat's ndc.z is LESS than the layer's depth at the pixel (engine.cc:298-299), and the
 // result is composited over the layer's colour instead of the clear colour.
-template <int MODE, bool LAYER>
-__global__ void __launch_bounds__(kBlendThreads, 1)
-k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ pair_rank,
-        const float4* __restrict__ rrec, int bgra, const unsigned long long* __restrict__ layer,
-        const float* __restrict__ zndc, uint8_t* __restrict__ image) {
+template <int MODE, bool LAYER, int ROWS>
+__global__ void __launch_bounds__(128 * ROWS, MODE == VKGSB_BLEND_FP32_MODE ? 1024 / (128 * ROWS) : 1)
+k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const uint2* __restrict__ ranges,
+        const uint32_t* __restrict__ pair_rank, const float4* __restrict__ rrec, int bgra, uint32_t reg_y0,
+        const unsigned long long* __restrict__ layer, const float* __restrict__ zndc, uint8_t* __restrict__ image) {
+  constexpr int THREADS = 128 * ROWS, RH = kSubH * ROWS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float4* s_q0 = reinterpret_cast<float4*>(smem_raw);
   float4* s_q1 = s_q0 + kBatch;
   float4* s_q2 = s_q1 + kBatch;
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_q2 + kBatch);
   float* s_z = reinterpret_cast<float*>(s_mask + kBatch);  // LAYER only
-  __shared__ uint32_t s_alive;
+  __shared__ uint32_t s_alive, s_redo;
 
   const uint32_t width = fpp->width, bins_x = fpp->bins_x;
   const uint32_t band_y0 = fpp->band_y0, band_y1 = fpp->band_y1;
-  const uint32_t bin = blockIdx.x, bin_x = (bin % bins_x) * kBinW, bin_y = (bin / bins_x + fpp->bin_y0) * kBinH;
+  const uint32_t reg = blockIdx.x, reg_x = (reg % bins_x) * kBinW, reg_y = (reg / bins_x + reg_y0) * RH;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t sub_x = bin_x + (warp % kSubCols) * kSubW, sub_y = bin_y + (warp / kSubCols) * kSubH;
+  const uint32_t sub_x = reg_x + (warp % kSubCols) * kSubW, sub_y = reg_y + (warp / kSubCols) * kSubH;
   const uint32_t x = sub_x + (lane & 15u), y_first = sub_y + (lane >> 4);
   const uint32_t org_y = sub_y & ~static_cast<uint32_t>(kTile - 1);  // 16-aligned origin (sub_x already is)
   const float tile_x = static_cast<float>(sub_x), tile_y = static_cast<float>(org_y);
@@ -100,9 +126,48 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
       }
     }
   }
-  uint2 range = ranges[((bin_y >> fpp->cshift_y) - fpp->cbin_y0) * fpp->cbins_x + (bin_x >> fpp->cshift_x)];
+  // the region lies inside one coarse bin (coarse bins are >= 128 x 128 pixels, aligned)
+  uint2 range = ranges[((reg_y >> fpp->cshift_y) - fpp->cbin_y0) * fpp->cbins_x + (reg_x >> fpp->cshift_x)];
   if (range.y < range.x) range.y = range.x;  // a bin no pair reached keeps end = 0 (bin.cu)
   const uint32_t wbit = 1u << warp;
+
+  // entries [b0, b0 + cnt) of the list -> shared memory, with their sub-tile masks (& keep)
+  auto stage = [&](uint32_t b0, uint32_t cnt, uint32_t keep) {
+    for (uint32_t i = tid; i < cnt; i += THREADS) {
+      const uint32_t rank = __ldg(pair_rank + b0 + i);
+      const float4 q0 = __ldg(rrec + rank * 3 + 0), q1 = __ldg(rrec + rank * 3 + 1), q2 = __ldg(rrec + rank * 3 + 2);
+      const uint32_t bxw = __float_as_uint(q2.z), byw = __float_as_uint(q2.w);
+      s_q0[i] = q0; s_q1[i] = q1; s_q2[i] = q2;
+      if (LAYER) s_z[i] = __ldg(zndc + rank);
+      s_mask[i] = subtile_mask<ROWS>(bxw & 0xffffu, bxw >> 16, byw & 0xffffu, byw >> 16, reg_x, reg_y) & keep;
+    }
+  };
+  // per-entry constants of the pinned fragment form
+  struct Entry {
+    float4 q0, q1;
+    float2 q2;
+    float bx, by, z;
+  };
+  auto entry = [&](uint32_t j) {
+    Entry e;
+    e.q0 = s_q0[j];
+    e.q1 = s_q1[j];
+    e.q2 = *reinterpret_cast<const float2*>(&s_q2[j]);
+    const float ox = __fsub_rn(tile_x, e.q1.x), oy = __fsub_rn(tile_y, e.q1.y);
+    e.bx = __fadd_rn(__fmul_rn(e.q0.x, ox), __fmul_rn(e.q0.y, oy));
+    e.by = __fadd_rn(__fmul_rn(e.q0.z, ox), __fmul_rn(e.q0.w, oy));
+    e.z = LAYER ? s_z[j] : 0.f;
+    return e;
+  };
+  // alpha of entry e at pixel k of this lane; false when the pixel is outside the +-3 sigma square / behind the layer
+  auto fragment = [&](const Entry& e, int k, float* al) {
+    const float px = fmaf(e.q0.x, flx, fmaf(e.q0.y, fly[k], e.bx));
+    const float py = fmaf(e.q0.z, flx, fmaf(e.q0.w, fly[k], e.by));
+    if (!(fabsf(px) <= 3.f && fabsf(py) <= 3.f && (!LAYER || e.z < ldepth[k]))) return false;
+    *al = __saturatef(e.q2.y * __expf(-0.5f * fmaf(py, py, px * px)));
+    return true;
+  };
+  uint32_t* img = reinterpret_cast<uint32_t*>(image);
 
   if (MODE == VKGSB_BLEND_FP32_MODE) {
     float T[kPix], cr[kPix], cg[kPix], cb[kPix], ca[kPix];
@@ -113,7 +178,7 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
       done[k] = !inside[k];
     }
     bool warp_done = __all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3]);
-    if (tid == 0) s_alive = 0xffffffffu;
+    if (tid == 0) s_alive = 0xffffffffu >> (32 - 4 * ROWS);
     __syncthreads();
     if (warp_done && lane == 0) atomicAnd(&s_alive, ~wbit);
     __syncthreads();
@@ -122,14 +187,7 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
       const uint32_t alive = s_alive;
       if (alive == 0u) break;
       const uint32_t cnt = min(static_cast<uint32_t>(kBatch), range.y - b0);
-      if (tid < cnt) {
-        const uint32_t rank = __ldg(pair_rank + b0 + tid);
-        const float4 q0 = __ldg(rrec + rank * 3 + 0), q1 = __ldg(rrec + rank * 3 + 1), q2 = __ldg(rrec + rank * 3 + 2);
-        const uint32_t bxw = __float_as_uint(q2.z), byw = __float_as_uint(q2.w);
-        s_q0[tid] = q0; s_q1[tid] = q1; s_q2[tid] = q2;
-        if (LAYER) s_z[tid] = __ldg(zndc + rank);
-        s_mask[tid] = subtile_mask(bxw & 0xffffu, bxw >> 16, byw & 0xffffu, byw >> 16, bin_x, bin_y) & alive;
-      }
+      stage(b0, cnt, alive);
       __syncthreads();
       if (!warp_done) {
         for (uint32_t g0 = 0; g0 < cnt && !warp_done; g0 += 32) {
@@ -138,22 +196,15 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
           while (bits) {
             const uint32_t j = g0 + __ffs(bits) - 1;
             bits &= bits - 1;
-            const float4 q0 = s_q0[j], q1 = s_q1[j];
-            const float2 q2 = *reinterpret_cast<const float2*>(&s_q2[j]);
-            const float ox = __fsub_rn(tile_x, q1.x), oy = __fsub_rn(tile_y, q1.y);
-            const float bx = __fadd_rn(__fmul_rn(q0.x, ox), __fmul_rn(q0.y, oy));
-            const float by = __fadd_rn(__fmul_rn(q0.z, ox), __fmul_rn(q0.w, oy));
-            const float z = LAYER ? s_z[j] : 0.f;
+            const Entry e = entry(j);
 #pragma unroll
             for (int k = 0; k < kPix; ++k) {
-              const float px = fmaf(q0.x, flx, fmaf(q0.y, fly[k], bx));
-              const float py = fmaf(q0.z, flx, fmaf(q0.w, fly[k], by));
-              if (!done[k] && fabsf(px) <= 3.f && fabsf(py) <= 3.f && (!LAYER || z < ldepth[k])) {
-                const float al = __saturatef(q2.y * __expf(-0.5f * fmaf(py, py, px * px)));
+              float al;
+              if (!done[k] && fragment(e, k, &al)) {
                 const float w = al * T[k];
-                cr[k] = fmaf(q1.z, w, cr[k]);
-                cg[k] = fmaf(q1.w, w, cg[k]);
-                cb[k] = fmaf(q2.x, w, cb[k]);
+                cr[k] = fmaf(e.q1.z, w, cr[k]);
+                cg[k] = fmaf(e.q1.w, w, cg[k]);
+                cb[k] = fmaf(e.q2.x, w, cb[k]);
                 ca[k] = fmaf(al, w, ca[k]);
                 T[k] -= w;
                 done[k] = T[k] < kTransmittanceCut;
@@ -169,7 +220,6 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
       }
       __syncthreads();
     }
-    uint32_t* img = reinterpret_cast<uint32_t*>(image);
 #pragma unroll
     for (int k = 0; k < kPix; ++k)
       if (inside[k]) {
@@ -182,97 +232,216 @@ k_blend(const FrameParams* __restrict__ fpp, const uint2* __restrict__ ranges, c
             pack_pixel(quantize8(cr[k]), quantize8(cg[k]), quantize8(cb[k]), quantize8(ca[k] + T[k]), bgra);
       }
   } else {
-    // back-to-front over the nearest-first list: batches from the tail, entries in reverse
-    float qr[kPix], qg[kPix], qb[kPix], qa[kPix];
+    // ---- phase A, front to back: transmittance only.  cut[k] = list position of the splat that took pixel k below
+    //      the transmittance cut (kNoCut: never - the pixel's walk starts at the far end, from the real background)
+    uint32_t cut[kPix];
+    uint32_t last_b0 = range.x;  // the last batch phase A staged (CTA-uniform)
+    {
+      float T[kPix];
+      bool done[kPix];
 #pragma unroll
-    for (int k = 0; k < kPix; ++k) {
-      qr[k] = static_cast<float>(lrgba[k] & 255u);
-      qg[k] = static_cast<float>((lrgba[k] >> 8) & 255u);
-      qb[k] = static_cast<float>((lrgba[k] >> 16) & 255u);
-      qa[k] = 255.f;
-    }
-    uint32_t remaining = range.y - range.x;
-    while (remaining > 0) {
-      const uint32_t cnt = min(static_cast<uint32_t>(kBatch), remaining);
-      const uint32_t b0 = range.x + remaining - cnt;
-      __syncthreads();
-      if (tid < cnt) {
-        const uint32_t rank = __ldg(pair_rank + b0 + tid);
-        const float4 q0 = __ldg(rrec + rank * 3 + 0), q1 = __ldg(rrec + rank * 3 + 1), q2 = __ldg(rrec + rank * 3 + 2);
-        const uint32_t bxw = __float_as_uint(q2.z), byw = __float_as_uint(q2.w);
-        s_q0[tid] = q0; s_q1[tid] = q1; s_q2[tid] = q2;
-        if (LAYER) s_z[tid] = __ldg(zndc + rank);
-        s_mask[tid] = subtile_mask(bxw & 0xffffu, bxw >> 16, byw & 0xffffu, byw >> 16, bin_x, bin_y);
+      for (int k = 0; k < kPix; ++k) {
+        T[k] = 1.f;
+        done[k] = !inside[k];
+        cut[k] = kNoCut;
+      }
+      bool warp_done = __all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3]);
+      if (tid == 0) {
+        s_alive = 0xffffffffu >> (32 - 4 * ROWS);
+        s_redo = 0u;
       }
       __syncthreads();
-      for (int g0 = static_cast<int>((cnt - 1) & ~31u); g0 >= 0; g0 -= 32) {
-        const uint32_t m = (g0 + lane < cnt) ? s_mask[g0 + lane] : 0u;
-        uint32_t bits = __ballot_sync(0xffffffffu, (m & wbit) != 0u);
-        while (bits) {
-          const uint32_t top = 31u - __clz(bits);
-          const uint32_t j = g0 + top;
-          bits &= ~(1u << top);
-          const float4 q0 = s_q0[j], q1 = s_q1[j];
-          const float2 q2 = *reinterpret_cast<const float2*>(&s_q2[j]);
-          const float ox = __fsub_rn(tile_x, q1.x), oy = __fsub_rn(tile_y, q1.y);
-          const float bx = __fadd_rn(__fmul_rn(q0.x, ox), __fmul_rn(q0.y, oy));
-          const float by = __fadd_rn(__fmul_rn(q0.z, ox), __fmul_rn(q0.w, oy));
-          const float r255 = __fmul_rn(255.f, q1.z), g255 = __fmul_rn(255.f, q1.w), b255 = __fmul_rn(255.f, q2.x);
-          const float z = LAYER ? s_z[j] : 0.f;
+      if (warp_done && lane == 0) atomicAnd(&s_alive, ~wbit);
+      __syncthreads();
+      for (uint32_t b0 = range.x; b0 < range.y; b0 += kBatch) {
+        const uint32_t alive = s_alive;
+        if (alive == 0u) break;
+        last_b0 = b0;
+        const uint32_t cnt = min(static_cast<uint32_t>(kBatch), range.y - b0);
+        stage(b0, cnt, alive);
+        __syncthreads();
+        if (!warp_done) {
+          for (uint32_t g0 = 0; g0 < cnt && !warp_done; g0 += 32) {
+            const uint32_t m = (g0 + lane < cnt) ? s_mask[g0 + lane] : 0u;
+            uint32_t bits = __ballot_sync(0xffffffffu, (m & wbit) != 0u);
+            while (bits) {
+              const uint32_t j = g0 + __ffs(bits) - 1;
+              bits &= bits - 1;
+              const Entry e = entry(j);
 #pragma unroll
-          for (int k = 0; k < kPix; ++k) {
-            const float px = fmaf(q0.x, flx, fmaf(q0.y, fly[k], bx));
-            const float py = fmaf(q0.z, flx, fmaf(q0.w, fly[k], by));
-            if (fabsf(px) <= 3.f && fabsf(py) <= 3.f && (!LAYER || z < ldepth[k])) {
-              const float al = __saturatef(q2.y * __expf(-0.5f * fmaf(py, py, px * px)));
-              const float om = __fsub_rn(1.f, al);
-              qr[k] = rintf(fmaf(r255, al, __fmul_rn(qr[k], om)));
-              qg[k] = rintf(fmaf(g255, al, __fmul_rn(qg[k], om)));
-              qb[k] = rintf(fmaf(b255, al, __fmul_rn(qb[k], om)));
-              qa[k] = rintf(fmaf(__fmul_rn(255.f, al), al, __fmul_rn(qa[k], om)));
+              for (int k = 0; k < kPix; ++k) {
+                float al;
+                if (!done[k] && fragment(e, k, &al)) {
+                  T[k] = __fmul_rn(T[k], __fsub_rn(1.f, al));
+                  if (T[k] < kTransmittanceCut) {
+                    done[k] = true;
+                    cut[k] = b0 + j;
+                  }
+                }
+              }
+              if (__all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3])) {
+                warp_done = true;
+                if (lane == 0) atomicAnd(&s_alive, ~wbit);
+                break;
+              }
             }
           }
         }
+        __syncthreads();
       }
-      remaining -= cnt;
     }
-    uint32_t* img = reinterpret_cast<uint32_t*>(image);
+    // ---- phase B, back to front from the cuts: both ends of the bracket through the exact recurrence
+    float lo[kPix][4], hi[kPix][4];
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) {
+      const bool open = cut[k] != kNoCut;
+      lo[k][0] = open ? 0.f : static_cast<float>(lrgba[k] & 255u);
+      lo[k][1] = open ? 0.f : static_cast<float>((lrgba[k] >> 8) & 255u);
+      lo[k][2] = open ? 0.f : static_cast<float>((lrgba[k] >> 16) & 255u);
+      lo[k][3] = open ? 0.f : 255.f;
+      hi[k][0] = open ? 255.f : lo[k][0];
+      hi[k][1] = open ? 255.f : lo[k][1];
+      hi[k][2] = open ? 255.f : lo[k][2];
+      hi[k][3] = 255.f;
+      if (!inside[k]) cut[k] = 0u;  // never drawn
+    }
+    auto walk = [&](uint32_t from_b0, bool whole_list) {
+      // the warp's deepest start; entries behind it are skipped without a look
+      uint32_t wcut = 0;
+#pragma unroll
+      for (int k = 0; k < kPix; ++k) wcut = max(wcut, whole_list ? (inside[k] ? kNoCut : 0u) : cut[k]);
+      wcut = __reduce_max_sync(0xffffffffu, wcut);
+      bool met = whole_list;  // warp-uniform: every pixel's ends have met - one state is enough from here on
+      for (uint32_t b0 = from_b0;; b0 -= kBatch) {
+        const uint32_t cnt = min(static_cast<uint32_t>(kBatch), range.y - b0);
+        __syncthreads();  // the previous batch has been consumed
+        stage(b0, cnt, 0xffffffffu);
+        __syncthreads();
+        if ((!whole_list || (s_redo & wbit)) && wcut >= b0) {
+          for (int g0 = static_cast<int>((cnt - 1) & ~31u); g0 >= 0; g0 -= 32) {
+            const uint32_t gi = b0 + g0 + lane;
+            const uint32_t m = (g0 + lane < cnt && gi <= wcut) ? s_mask[g0 + lane] : 0u;
+            uint32_t bits = __ballot_sync(0xffffffffu, (m & wbit) != 0u);
+            while (bits) {
+              const uint32_t top = 31u - __clz(bits);
+              const uint32_t j = g0 + top;
+              bits &= ~(1u << top);
+              const Entry e = entry(j);
+              const float s255[4] = {__fmul_rn(255.f, e.q1.z), __fmul_rn(255.f, e.q1.w), __fmul_rn(255.f, e.q2.x), 0.f};
+              if (!met) {
+#pragma unroll
+                for (int k = 0; k < kPix; ++k) {
+                  float al;
+                  if ((whole_list || b0 + j <= cut[k]) && fragment(e, k, &al)) {
+                    const float om = __fsub_rn(1.f, al), a255 = __fmul_rn(255.f, al);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                      const float s = c < 3 ? s255[c] : a255;
+                      lo[k][c] = rint255(fmaf(s, al, __fmul_rn(lo[k][c], om)));
+                      hi[k][c] = rint255(fmaf(s, al, __fmul_rn(hi[k][c], om)));
+                    }
+                  }
+                }
+                bool same = true;
+#pragma unroll
+                for (int k = 0; k < kPix; ++k)
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) same = same && lo[k][c] == hi[k][c];
+                // once met, always met; a pixel still waiting for its (nearer) cut holds 0 / 255: not met
+                met = __all_sync(0xffffffffu, same);
+              } else {
+#pragma unroll
+                for (int k = 0; k < kPix; ++k) {
+                  float al;
+                  if (fragment(e, k, &al)) {
+                    const float om = __fsub_rn(1.f, al), a255 = __fmul_rn(255.f, al);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                      const float s = c < 3 ? s255[c] : a255;
+                      lo[k][c] = rint255(fmaf(s, al, __fmul_rn(lo[k][c], om)));
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (b0 == range.x) break;
+      }
+      if (met) {
+#pragma unroll
+        for (int k = 0; k < kPix; ++k)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) hi[k][c] = lo[k][c];
+      }
+    };
+    if (range.y > range.x) {
+      walk(last_b0, false);
+      bool bad = false;
+#pragma unroll
+      for (int k = 0; k < kPix; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bad = bad || (inside[k] && lo[k][c] != hi[k][c]);
+      if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_redo, wbit);
+      __syncthreads();
+      // ---- phase C (rare): a bracket stayed open at the front of the list -> the exact full walk for that warp
+      if (s_redo != 0u) {
+        if (s_redo & wbit) {
+#pragma unroll
+          for (int k = 0; k < kPix; ++k) {
+            lo[k][0] = hi[k][0] = static_cast<float>(lrgba[k] & 255u);
+            lo[k][1] = hi[k][1] = static_cast<float>((lrgba[k] >> 8) & 255u);
+            lo[k][2] = hi[k][2] = static_cast<float>((lrgba[k] >> 16) & 255u);
+            lo[k][3] = hi[k][3] = 255.f;
+          }
+          if (lane == 0) atomicAdd(&ctrl->blend_full_walks, 1u);
+        }
+        walk(range.x + ((range.y - 1 - range.x) / kBatch) * kBatch, true);
+      }
+    }
 #pragma unroll
     for (int k = 0; k < kPix; ++k)
       if (inside[k])
         img[static_cast<size_t>(y_first + 2 * k) * width + x] =
-            pack_pixel(clamp255(qr[k]), clamp255(qg[k]), clamp255(qb[k]), clamp255(qa[k]), bgra);
+            pack_pixel(clamp255(lo[k][0]), clamp255(lo[k][1]), clamp255(lo[k][2]), clamp255(lo[k][3]), bgra);
   }
 }
 
-void blend_configure() {
-  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_FP32_MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmem);
-  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_UNORM8_MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmem);
-  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_FP32_MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmemLayer);
-  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_UNORM8_MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmemLayer);
+template <int MODE, bool LAYER, int ROWS>
+static void blend_launch(const FrameParams* d_fp, const FrameParams& h_fp, Control* d_ctrl, const uint2* d_ranges,
+                         const uint32_t* d_pair_rank, const float4* rrec, int bgra, const unsigned long long* d_layer,
+                         const float* d_zndc, uint8_t* d_image, cudaStream_t stream) {
+  constexpr uint32_t RH = kSubH * ROWS;
+  if (h_fp.band_y1 <= h_fp.band_y0) return;
+  const uint32_t ry0 = h_fp.band_y0 / RH, ry1 = (h_fp.band_y1 + RH - 1) / RH;
+  const uint32_t nreg = h_fp.bins_x * (ry1 - ry0);
+  if (nreg == 0) return;
+  k_blend<MODE, LAYER, ROWS><<<nreg, 128 * ROWS, blend_smem(LAYER), stream>>>(d_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra,
+                                                                            ry0, d_layer, d_zndc, d_image);
 }
 
-void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_rank,
-                  const float* d_rrec, int blend_mode, int bgra, const unsigned long long* d_layer, const float* d_zndc,
-                  uint8_t* d_image, cudaStream_t stream) {
-  const uint32_t nbins = h_fp.bins_x * (h_fp.bin_y1 - h_fp.bin_y0);
-  if (nbins == 0) return;
+void blend_configure() {
+  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_FP32_MODE, false, kRowsFp32>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(false));
+  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_UNORM8_MODE, false, kRowsUnorm8>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(false));
+  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_FP32_MODE, true, kRowsFp32>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(true));
+  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_UNORM8_MODE, true, kRowsUnorm8>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(true));
+}
+
+void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, Control* d_ctrl, const uint2* d_ranges,
+                  const uint32_t* d_pair_rank, const float* d_rrec, int blend_mode, int bgra,
+                  const unsigned long long* d_layer, const float* d_zndc, uint8_t* d_image, cudaStream_t stream) {
   const float4* rrec = reinterpret_cast<const float4*>(d_rrec);
   const bool layer = d_layer != nullptr && d_zndc != nullptr;
   if (blend_mode == VKGSB_BLEND_FP32_MODE) {
     if (layer)
-      k_blend<VKGSB_BLEND_FP32_MODE, true><<<nbins, kBlendThreads, kBlendSmemLayer, stream>>>(
-          d_fp, d_ranges, d_pair_rank, rrec, bgra, d_layer, d_zndc, d_image);
+      blend_launch<VKGSB_BLEND_FP32_MODE, true, kRowsFp32>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, d_layer, d_zndc, d_image, stream);
     else
-      k_blend<VKGSB_BLEND_FP32_MODE, false><<<nbins, kBlendThreads, kBlendSmem, stream>>>(
-          d_fp, d_ranges, d_pair_rank, rrec, bgra, nullptr, nullptr, d_image);
+      blend_launch<VKGSB_BLEND_FP32_MODE, false, kRowsFp32>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, nullptr, nullptr, d_image, stream);
   } else {
     if (layer)
-      k_blend<VKGSB_BLEND_UNORM8_MODE, true><<<nbins, kBlendThreads, kBlendSmemLayer, stream>>>(
-          d_fp, d_ranges, d_pair_rank, rrec, bgra, d_layer, d_zndc, d_image);
+      blend_launch<VKGSB_BLEND_UNORM8_MODE, true, kRowsUnorm8>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, d_layer, d_zndc, d_image, stream);
     else
-      k_blend<VKGSB_BLEND_UNORM8_MODE, false><<<nbins, kBlendThreads, kBlendSmem, stream>>>(
-          d_fp, d_ranges, d_pair_rank, rrec, bgra, nullptr, nullptr, d_image);
+      blend_launch<VKGSB_BLEND_UNORM8_MODE, false, kRowsUnorm8>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, nullptr, nullptr, d_image, stream);
   }
 }
 

@@ -79,7 +79,7 @@ struct Control {
   uint32_t visible_count;   // V  (VisiblePointCount, rank.comp:38)
   uint32_t pair_count;      // D
   uint32_t pair_overflow;
-  uint32_t project_ticket;
+  uint32_t blend_full_walks; // UNORM8 blend: warps whose bracket stayed open and walked their whole list (blend.cu)
   uint32_t tile_cut;        // binning tiles [0, tile_cut) fit in max_pairs (bin.cu)
   uint32_t partial_pairs;   // pairs kept of the last kept tile when the capacity cut falls inside it
   uint32_t bin_items;       // work items of k_bin_count / k_bin_place

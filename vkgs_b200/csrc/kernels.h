@@ -26,12 +26,27 @@ void launch_export_scene(const SceneStorage& src, uint32_t n, float* d_pos, floa
                          uint16_t* d_sh, cudaStream_t stream);
 
 // ---- project.cu ------------------------------------------------------------------------------------------------
-uint32_t project_num_tiles(uint32_t n);  // scan descriptors k_project needs
-// d_rrec: 3 x float4 raster record per visible slot; d_inst: 12-float instance record (written only when
-// FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control.
-void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl, unsigned long long* d_scan_desc,
-                    uint32_t* d_keys, uint32_t* d_slots, uint32_t* d_vis_id, float* d_rrec, uint32_t* d_bin_rect,
-                    float* d_inst, float* d_zndc, cudaStream_t stream);
+int sm_count();                          // SMs of the current device (cached)
+uint32_t project_num_tiles(uint32_t n);  // tiles of 256 splats
+// What k_cull leaves for k_project: a visibility bit per splat and a 32-ary tree of visible counts over the tiles.
+struct CullIndex {
+  uint32_t* mask;      // [tiles * 8]  bit (id & 31) of word id >> 5
+  uint32_t* tile_cnt;  // [tiles]      visible splats per tile
+  uint32_t* lvl_a;     // [na] sums over 32 tiles      } zero on entry
+  uint32_t* lvl_b;     // [nb] sums over 32 A entries  }
+  uint32_t* lvl_c;     // [nc] sums over 32 B entries  }
+};
+struct CullIndexLayout {
+  uint32_t tiles, na, nb, nc;
+};
+CullIndexLayout cull_index_layout(uint32_t max_splats);
+void project_configure();  // once per device: opt in to > 48 KB dynamic shared memory
+// k_cull + k_project.  d_rrec: 3 x float4 raster record per visible slot; d_inst: 12-float instance record (written only
+// when FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control and writes
+// Control::visible_count.
+void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl, const CullIndex& ix, uint32_t* d_keys,
+                    uint32_t* d_slots, uint32_t* d_vis_id, float* d_rrec, uint32_t* d_bin_rect, float* d_inst,
+                    float* d_zndc, cudaStream_t stream);
 
 // ---- sort.cu: onesweep LSD radix sort, count read on the device ----------------------------------------------------
 struct SortArgs {
@@ -82,9 +97,9 @@ void launch_lines(const FrameParams* d_fp, uint32_t n_lines, const float* d_pos,
 
 // d_ranges: [begin,end) of every coarse bin in d_pair_slot
 // d_layer / d_zndc: both null, or the line layer and the splats' ndc.z by slot (depth test LESS against the layer)
-void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, const uint2* d_ranges, const uint32_t* d_pair_slot,
-                  const float* d_rrec, int blend_mode, int bgra, const unsigned long long* d_layer, const float* d_zndc,
-                  uint8_t* d_image, cudaStream_t stream);
+void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, Control* d_ctrl, const uint2* d_ranges,
+                  const uint32_t* d_pair_slot, const float* d_rrec, int blend_mode, int bgra,
+                  const unsigned long long* d_layer, const float* d_zndc, uint8_t* d_image, cudaStream_t stream);
 
 // ---- misc ----------------------------------------------------------------------------------------------------------
 void launch_row_histogram(const Control* d_ctrl, const float* d_rrec, uint32_t max_visible, uint32_t height,

@@ -69,10 +69,10 @@ struct vkgsb_renderer {
   uint32_t* bin_slots = nullptr;   // splat slots by coarse bin, nearest first (bin.cu); capacity max_pairs
   BinScratch bin{};
   uint32_t* lookback_depth = nullptr;
-  uint8_t* zero_region = nullptr;  // Control | scan descriptors (project) | coarse-bin ranges
+  uint8_t* zero_region = nullptr;  // Control | upper levels of the cull index's count tree | coarse-bin ranges
   size_t zero_bytes = 0;
   Control* ctrl = nullptr;
-  unsigned long long* desc_project = nullptr;
+  CullIndex cull{};                // k_cull -> k_project (project.cu)
   uint2* ranges = nullptr;
   FrameParams* d_fp = nullptr;
   uint8_t* image = nullptr;
@@ -336,7 +336,7 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   if (r->n_lines) launch_lines(r->d_fp, r->n_lines, r->line_pos, r->line_col, r->width, r->height, r->layer, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[0], s));
   // the depth sort runs an odd number of passes: its input goes to the ping-pong side, its result lands in keys / slots
-  launch_project(sc, r->d_fp, r->ctrl, r->desc_project, r->keys_alt, r->slots_alt, r->vis_id, r->rrec, r->bin_rect, r->inst,
+  launch_project(sc, r->d_fp, r->ctrl, r->cull, r->keys_alt, r->slots_alt, r->vis_id, r->rrec, r->bin_rect, r->inst,
                  r->n_lines ? r->zndc : nullptr, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
   SortArgs depth{};
@@ -355,11 +355,11 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   if (timed) CU_TRY(cudaEventRecord(r->ev[2], s));
   launch_bin(r->d_fp, r->h_fp.ncbins, r->ctrl, r->slots, r->bin_rect, n, r->max_pairs, r->bin, r->ranges, r->bin_slots, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[3], s));
-  launch_blend(r->d_fp, r->h_fp, r->ranges, r->bin_slots, r->rrec, r->blend_mode,
+  launch_blend(r->d_fp, r->h_fp, r->ctrl, r->ranges, r->bin_slots, r->rrec, r->blend_mode,
                r->pixel_format == VKGSB_FORMAT_BGRA8, r->n_lines ? r->layer : nullptr, r->n_lines ? r->zndc : nullptr,
                r->image, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[4], s));
-  CU_TRY(cudaMemcpyAsync(r->h_counts, r->ctrl, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(r->h_counts, r->ctrl, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaGetLastError());
   return VKGSB_OK;
 }
@@ -474,13 +474,18 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   ALLOC(r->bin.tile_bin, static_cast<size_t>(kMaxCoarseBins) * r->bin.tile_stride * 4);
   ALLOC(r->bin.bin_total, kMaxCoarseBins * 4);
   ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats));
-  const size_t nb_proj = project_num_tiles(r->max_splats);
+  const CullIndexLayout cl = cull_index_layout(r->max_splats);
   const size_t ctrl_bytes = (sizeof(Control) + 255) & ~size_t(255);
-  r->zero_bytes = ctrl_bytes + nb_proj * 8 + kMaxCoarseBins * sizeof(uint2);
+  const size_t tree_words = (static_cast<size_t>(cl.na) + cl.nb + cl.nc + 63) & ~size_t(63);
+  r->zero_bytes = ctrl_bytes + tree_words * 4 + kMaxCoarseBins * sizeof(uint2);
   ALLOC(r->zero_region, r->zero_bytes);
   r->ctrl = reinterpret_cast<Control*>(r->zero_region);
-  r->desc_project = reinterpret_cast<unsigned long long*>(r->zero_region + ctrl_bytes);
-  r->ranges = reinterpret_cast<uint2*>(r->desc_project + nb_proj);
+  r->cull.lvl_a = reinterpret_cast<uint32_t*>(r->zero_region + ctrl_bytes);
+  r->cull.lvl_b = r->cull.lvl_a + cl.na;
+  r->cull.lvl_c = r->cull.lvl_b + cl.nb;
+  r->ranges = reinterpret_cast<uint2*>(r->cull.lvl_a + tree_words);
+  ALLOC(r->cull.mask, static_cast<size_t>(cl.tiles) * 8 * 4);
+  ALLOC(r->cull.tile_cnt, static_cast<size_t>(cl.tiles) * 4);
   ALLOC(r->d_fp, sizeof(FrameParams));
   ALLOC(r->image, static_cast<size_t>(r->max_width) * r->max_height * 4);
   ALLOC(r->stage[0], static_cast<size_t>(r->max_width) * r->max_height * 4);
@@ -494,6 +499,7 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   for (auto& ev : r->chunk_done)
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   blend_configure();
+  project_configure();
   r->loader = std::thread(loader_main, r);
   *out = r;
   return VKGSB_OK;
@@ -516,7 +522,7 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
   void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
                  r->vis_id, r->inst, r->rrec, r->bin_rect, r->bin_slots, r->bin.tile_pairs, r->bin.tile_item, r->bin.tile_bin, r->bin.bin_total,
-                 r->lookback_depth, r->zero_region, r->d_fp, r->image, r->stage[0], r->stage[1], r->d_offsets, r->d_rows[0],
+                 r->lookback_depth, r->zero_region, r->cull.mask, r->cull.tile_cnt, r->d_fp, r->image, r->stage[0], r->stage[1], r->d_offsets, r->d_rows[0],
                  r->d_rows[1], r->line_pos, r->line_col, r->zndc, r->layer};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -743,6 +749,7 @@ int vkgsb_get_stats(vkgsb_renderer* r, vkgsb_stats* out) {
   out->visible_point_count = r->h_counts[0];
   out->pair_count = r->h_counts[1];
   out->pair_overflow = r->h_counts[2];
+  out->blend_full_walks = r->h_counts[3];
   out->frame_counter = r->frame_counter;
   if (r->ev_recorded) {
     CU_TRY(cudaEventElapsedTime(&out->ms_project, r->ev[0], r->ev[1]));

@@ -386,9 +386,9 @@ __global__ void __launch_bounds__(kSortThreads, 4) k_sort_onesweep(SortArgs a, i
 void launch_sort(const SortArgs& a, cudaStream_t stream) {
   if (a.max_n == 0) return;
   const uint32_t parts = sort_max_parts(a.max_n);
-  int hist_blocks = static_cast<int>(min(static_cast<uint32_t>(148 * 8), (a.max_n + 4095u) / 4096u));
+  int hist_blocks = static_cast<int>(min(static_cast<uint32_t>(sm_count() * 8), (a.max_n + 4095u) / 4096u));
   if (!a.have_hist) k_sort_hist<<<hist_blocks, 256, 0, stream>>>(a);
-  int blocks = static_cast<int>(min(parts, static_cast<uint32_t>(148 * 4)));
+  int blocks = static_cast<int>(min(parts, static_cast<uint32_t>(sm_count() * 4)));
   for (int p = 0; p < a.npass; ++p) {
     int shift;
     uint32_t bin0;
