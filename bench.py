@@ -1,25 +1,29 @@
 #!/usr/bin/env python
-"""Headline benchmark: frames/s at 1600x900 on the 6.1 M-splat SH3 synthetic 'bicycle' scene (BASELINE.json
-configs[1]) through the C ABI of libvkgsb.so.  One JSON line on stdout (rank 0).
+"""Benchmarks of the frame path through the C ABI of libvkgsb.so.  One JSON line on stdout (rank 0).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c4|c5]
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one frame: camera block in, project -> sort -> bin -> blend, RGBA8 image out.  Views are sharded across
-ranks (weak scaling: K frames per rank, different cameras), images gathered to rank 0 with NCCL.
+  c2 (default, the headline; BASELINE.json configs[1]): frames/s at 1600x900 on the 6.1 M-splat SH3 'bicycle' scene.
+      A step = one frame: camera block in, cull -> project -> sort -> bin -> blend, RGBA8 image out.  Views are sharded
+      across ranks in contiguous blocks (weak scaling: K frames per rank), finished images delivered to rank 0.
+      `value` is measured with the fp32 blend (VKGSB_BLEND_FP32); the reference-faithful VKGSB_BLEND_UNORM8 mode
+      (B8G8R8A8_UNORM target, render_pass.cc:15) is timed the same way and reported beside it as `value_unorm8`,
+      `stages_ms_unorm8`, `e2e_unorm8`.
+  c4 (configs[3]): the same scene, 360-view orbit at 3840x2160 sharded by camera.
+  c5 (configs[4]): 50 M splats at 3840x2160 in screen-tile bands, one band per GPU (strong scaling of one frame).
 `--impl reference` times the CPU restatement of the reference's shaders (oracle/, OpenMP on all host cores; the
-reference's Vulkan build is not runnable here) on a bounded sample of the same workload.
+reference's Vulkan build is not runnable on this image: no loader, ICD or SDK, profiles/r02_host_vulkan_probe.txt) on a
+bounded sample of the same workload.
 """
 from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -27,23 +31,39 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "fps_1600x900_6.1M_splats_sh3"
 UNIT = "frames/s"
-WIDTH, HEIGHT = 1600, 900
-N_SPLATS = 6_131_954
-N_VIEWS = 64                      # orbit the steps cycle through
-ORBIT = dict(r=1.5, phi_deg=70.0)  # ~2 M visible of 6.1 M: the reference's "view 2" regime (DETAILS.md:72)
-E2E_BATCH = 8                     # views per vkgsb_draw_batch call in the end-to-end leg
 PARAM_BYTES = 548                 # sizeof(FrameParams): the per-frame host->device upload (a kernel argument)
-WORKLOAD = ("C2 bicycle-shaped 6,131,954 splats SH3, 1600x900, 64-view orbit r=1.5 phi=70deg "
-            "(~2 M visible, the reference's 'view 2' regime)")
-KERNELS_PER_FRAME = 9             # set_params, project, 3 depth onesweep passes, bin count / scan / place, blend
+E2E_BATCH = 8                     # views per vkgsb_draw_batch call in the end-to-end leg
+SMEM_BYTES_PER_ENTRY = 52         # blend stage: 3 x float4 raster record + 4-byte sub-tile mask per staged list entry
+FP32_INSTR_PER_FRAGMENT = 20      # algorithmic FP32 instructions per fragment (the blend roofline's unit)
+
+CONFIGS = {
+    "c2": dict(metric="fps_1600x900_6.1M_splats_sh3", width=1600, height=900, n_splats=6_131_954, scene="bicycle",
+               n_views=64, orbit=dict(r=1.5, phi_deg=70.0), theta0=30.0, max_pairs=64_000_000, scaling="weak",
+               workload=("C2 bicycle-shaped 6,131,954 splats SH3, 1600x900, 64-view orbit r=1.5 phi=70deg "
+                         "(~2 M visible, the reference's 'view 2' regime)")),
+    "c4": dict(metric="views_per_s_3840x2160_6.1M_splats_orbit360", width=3840, height=2160, n_splats=6_131_954,
+               scene="bicycle", n_views=360, orbit=dict(r=4.0, phi_deg=70.0), theta0=0.0, max_pairs=128_000_000,
+               scaling="strong",
+               workload="C4 bicycle-shaped 6,131,954 splats SH3, 3840x2160, 360-view orbit r=4 phi=70deg sharded by camera"),
+    "c5": dict(metric="fps_3840x2160_50M_splats_bands", width=3840, height=2160, n_splats=50_000_000, scene="large",
+               n_views=8, orbit=dict(r=6.0, phi_deg=70.0), theta0=30.0, max_pairs=400_000_000, scaling="strong",
+               workload="C5 50,000,000 splats SH3 (70 % background), 3840x2160, camera r=6, one screen band per GPU"),
+}
+# kernels of one frame: set_params, cull, project, 3 depth onesweep passes, bin tiles / scan / place, blend
+KERNELS_PER_FRAME = 10
 
 
-def view_camera(i):
+def view_camera(cfg, i):
     from vkgs_b200 import camera as pycam
-    cam = pycam.orbit(WIDTH, HEIGHT, r=ORBIT["r"], phi_deg=ORBIT["phi_deg"], theta_deg=30.0 + 360.0 * (i % N_VIEWS) / N_VIEWS)
+    cam = pycam.orbit(cfg["width"], cfg["height"], theta_deg=cfg["theta0"] + 360.0 * (i % cfg["n_views"]) / cfg["n_views"],
+                      **cfg["orbit"])
     return cam.projection_matrix(), cam.view_matrix(), cam.eye()
+
+
+def make_scene(cfg):
+    from vkgs_b200 import synth
+    return synth.scene_bicycle(cfg["n_splats"]) if cfg["scene"] == "bicycle" else synth.scene_large(cfg["n_splats"])
 
 
 class ClockSampler:
@@ -134,8 +154,8 @@ def measured_peaks():
 
 
 def ncu_traffic():
-    """dram__bytes_read + dram__bytes_write per k_project launch, from the newest committed `ncu --set full` capture
-    (tools/ncu_traffic.py -> profiles/*_k_project_traffic.json); None when no capture is committed."""
+    """dram__bytes_read + dram__bytes_write of the projection stage's kernels per frame, from the newest committed
+    `ncu --set full` capture (tools/ncu_traffic.py -> profiles/*_k_project_traffic.json); None when none is committed."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_k_project_traffic.json")))
     if not files:
@@ -147,81 +167,169 @@ def ncu_traffic():
         return None, None
 
 
-def cpu_sample(rows_fn, threads_note=""):
-    """CPU restatement of the reference path (oracle, OpenMP) on a bounded sample: the whole cull / sort / projection
-    of one frame, and the rasteriser on a 16-row band scaled to the frame height."""
+# ------------------------------------------------------------------------------------------------- the CPU arm
+def cpu_sample(cfg, rows, view=0, state=None):
+    """One step of the CPU arm: the CPU restatement of the reference path (oracle/, C + OpenMP on all host cores) on a
+    bounded sample of one frame of the workload - the whole cull, sort and projection of the view, and the rasteriser
+    (the reference's UNORM8 blend, mode 1) on 8 bands of 16 rows spread evenly over the image height, scaled to the
+    full height.  Returns (frames/s estimate, seconds this step really took, description)."""
     from oracle import oracle as O
     from vkgs_b200 import synth
     O.use_all_cores()
-    rows = rows_fn()
+    w, h = cfg["width"], cfg["height"]
+    if state is None:
+        state = {}
+    if "scene" not in state:
+        state["scene"] = O.activate(rows, synth.STANDARD_OFFSETS)
+    scene = state["scene"]
     t0 = time.perf_counter()
-    scene = O.activate(rows, synth.STANDARD_OFFSETS)
-    del rows
-    P, V, E = view_camera(0)
-    cam = O.make_camera(P, V, E, WIDTH, HEIGHT)
-    t1 = time.perf_counter()
+    P, V, E = view_camera(cfg, view)
+    cam = O.make_camera(P, V, E, w, h)
     keys, ids = O.cull(scene, O.compose_pvm(P, V))
-    t2 = time.perf_counter()
+    t1 = time.perf_counter()
     keys, ids = O.sort_pairs(keys, ids)
-    t3 = time.perf_counter()
+    t2 = time.perf_counter()
     inst = O.project(scene, ids, cam, 0)
+    t3 = time.perf_counter()
+    nb, band_rows = 8, 16
+    starts = [((h - band_rows) * (2 * b + 1) // (2 * nb)) // 16 * 16 for b in range(nb)]
+    for y0 in starts:
+        O.raster_rows(inst, w, h, y0, y0 + band_rows, mode=1)
     t4 = time.perf_counter()
-    band = (HEIGHT // 2 // 16) * 16
-    rows_sampled = 16 * max(1, O.num_threads())           # one tile band per thread
-    rows_sampled = min(rows_sampled, 128)
-    r0 = max(0, band - rows_sampled // 2)
-    O.raster_rows(inst, WIDTH, HEIGHT, r0, r0 + rows_sampled, mode=0)
-    t5 = time.perf_counter()
-    raster_full = (t5 - t4) * HEIGHT / rows_sampled
-    frame_s = (t2 - t1) + (t3 - t2) + (t4 - t3) + raster_full
-    return dict(value=1.0 / frame_s, unit=UNIT, cores=O.num_threads(), kind="port",
-                sample=(f"1 frame, view 0, V={len(ids)}: full cull {1e3*(t2-t1):.0f} ms + sort {1e3*(t3-t2):.0f} ms + "
-                        f"projection {1e3*(t4-t3):.0f} ms; rasteriser on rows [{r0},{r0+rows_sampled}) "
-                        f"{1e3*(t5-t4):.0f} ms scaled x{HEIGHT/rows_sampled:.1f} (mid-frame band)"),
-                frame_ms_estimate=1e3 * frame_s), len(ids)
+    sampled = nb * band_rows
+    frame_s = (t3 - t0) + (t4 - t3) * h / sampled
+    desc = (f"1 frame of view {view}, V={len(ids)}: full cull {1e3*(t1-t0):.0f} ms + sort {1e3*(t2-t1):.0f} ms + projection "
+            f"{1e3*(t3-t2):.0f} ms; rasteriser (UNORM8 blend) on {nb} bands of {band_rows} rows at y={starts} "
+            f"{1e3*(t4-t3):.0f} ms scaled x{h/sampled:.2f}")
+    return 1.0 / frame_s, t4 - t0, desc, O.num_threads()
 
 
-def run_reference(args):
+def run_reference(args, cfg):
+    """The reference arm: K steps of the bounded CPU sample (a different orbit view each step); `value` is the frame rate
+    the samples extrapolate to, `ms_per_step` what a step really took (so steps x ms_per_step is the run's wall time)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from vkgs_b200 import synth
-    rows_holder = {}
-
-    def rows_fn():
-        if "r" not in rows_holder:
-            rows_holder["r"] = synth.scene_bicycle(N_SPLATS)
-        return rows_holder["r"]
-
-    vals = []
-    cb = None
-    for i in range(max(1, min(args.steps, 3)) + min(args.warmup, 1)):
-        cb, v = cpu_sample(rows_fn)
-        vals.append(cb["value"])
-    value = float(np.mean(vals[min(args.warmup, 1):]))
-    cb["value"] = value
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_view": 0,
-                       "note": "CPU restatement of the reference's shaders (oracle/, C + OpenMP); the reference's Vulkan "
-                               "build / lavapipe is not available on this image"},
-            "cpu_baseline": cb,
+    rows = make_scene(cfg)
+    state, vals, secs, desc, cores = {}, [], [], "", 1
+    steps = max(1, args.steps)
+    warm = max(0, min(args.warmup, 2))
+    budget_s = 240.0
+    t_begin = time.perf_counter()
+    done = 0
+    for i in range(warm + steps):
+        fps, s, desc, cores = cpu_sample(cfg, rows, view=(i * 7) % cfg["n_views"], state=state)
+        if i >= warm:
+            vals.append(fps); secs.append(s); done += 1
+        if time.perf_counter() - t_begin > budget_s and done >= 1:
+            break
+    value = float(1.0 / np.mean(1.0 / np.asarray(vals)))      # frames / total estimated seconds
+    line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": done, "warmup": warm, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
+            "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": desc + f"; {done} such steps (requested {steps}), frame_ms_estimate "
+                                              f"{1e3/value:.0f}; the reference's own Vulkan path cannot run here "
+                                              "(no Vulkan loader / lavapipe ICD / SDK on the box)",
+                             "frame_ms_estimate": 1e3 / value},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------- delivery to rank 0
+class NcclGather:
+    """Finished images go to rank 0 in batches of `every` frames; the gather of one batch (NCCL, its own stream)
+    overlaps the rendering of the next into the other buffer."""
+    name = "images gathered to rank 0 (NCCL, batches of 4 frames, double-buffered)"
+
+    def __init__(self, torch, dist, dev, world, rank, h, w, every=4, nbuf=2):
+        self.dist, self.world, self.rank, self.every, self.nbuf = dist, world, rank, every, nbuf
+        self.batches = [torch.empty((every, h, w, 4), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+        self.gathered = [[torch.empty_like(self.batches[0]) for _ in range(world)] if (world > 1 and rank == 0) else None
+                         for _ in range(nbuf)]
+        self.pending = [None] * nbuf
+
+    def dst(self, i):
+        b, j = (i // self.every) % self.nbuf, i % self.every
+        if j == 0 and self.pending[b] is not None:   # the buffer's previous gather must have read it
+            self.pending[b].wait()
+            self.pending[b] = None
+        return self.batches[b][j].data_ptr()
+
+    def sent(self, i):
+        b, j = (i // self.every) % self.nbuf, i % self.every
+        if self.world > 1 and j == self.every - 1:
+            self.pending[b] = self.dist.gather(self.batches[b], self.gathered[b], dst=0, async_op=True)
+
+    def drain(self):
+        for b in range(self.nbuf):
+            if self.pending[b] is not None:
+                self.pending[b].wait()
+                self.pending[b] = None
+
+
+class PeerWrite:
+    """Every rank renders straight into rank 0's memory: rank 0 allocates one buffer of `slots` x world images and
+    exports it (CUDA IPC through the C ABI, vkgsb_shared_*); the other ranks map it and pass `their slot` as the frame's
+    destination, so the blend kernel's pixel stores travel over NVLink and no kernel, copy or NCCL call runs on rank 0
+    for the delivery.  A barrier every `slots` steps keeps a slot from being overwritten before rank 0 is done with it
+    (never reached inside a timed region shorter than `slots` steps)."""
+    name = "every rank's blend kernel writes its pixels into rank 0's buffer over NVLink (CUDA IPC peer mapping, no NCCL on the data path)"
+
+    def __init__(self, torch, dist, dev, world, rank, h, w, local, slots):
+        import vkgs_b200
+        self.dist, self.world, self.rank, self.slots = dist, world, rank, slots
+        self.img = h * w * 4
+        self.V = vkgs_b200
+        if rank == 0:
+            self.base, handle = vkgs_b200.shared_create(local, slots * world * self.img)
+        else:
+            self.base, handle = 0, b""
+        obj = [handle]
+        if world > 1:
+            dist.broadcast_object_list(obj, src=0)
+        if rank != 0:
+            self.base = vkgs_b200.shared_open(local, obj[0])
+        self.local = local
+
+    def dst(self, i):
+        if self.world > 1 and i > 0 and i % self.slots == 0:
+            self.dist.barrier()
+        return self.base + ((i % self.slots) * self.world + self.rank) * self.img
+
+    def sent(self, i):
+        pass
+
+    def drain(self):
+        pass
+
+    def close(self):
+        if self.rank == 0:
+            self.V.shared_destroy(self.local, self.base)
+        else:
+            self.V.shared_close(self.local, self.base)
+
+
+# ------------------------------------------------------------------------------------------------- the GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--blend", default="fp32", choices=["fp32", "unorm8"])
+    ap.add_argument("--blend", default="fp32", choices=["fp32", "unorm8"], help="blend mode of the headline `value`")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="how finished images reach rank 0 (N > 1)")
+    ap.add_argument("--n-splats", type=int, default=0, help="override the scene size (experiments)")
     args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.n_splats:
+        cfg["n_splats"] = args.n_splats
+        cfg["workload"] += f" [scene size overridden: {args.n_splats}]"
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, cfg)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -230,7 +338,6 @@ def main():
     import vkgs_b200
     from vkgs_b200 import _lib as L
     from vkgs_b200 import dist as vdist
-    from vkgs_b200 import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -242,156 +349,312 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    K, W = args.steps, args.warmup
-    rows = synth.scene_bicycle(N_SPLATS)
-    r = vkgs_b200.Renderer(device=local, max_splats=N_SPLATS, max_width=WIDTH, max_height=HEIGHT, max_pairs=64_000_000)
+    W_, H_ = cfg["width"], cfg["height"]
+    rows = make_scene(cfg)
+    r = vkgs_b200.Renderer(device=local, max_splats=cfg["n_splats"], max_width=W_, max_height=H_, max_pairs=cfg["max_pairs"])
     r.upload_splats(rows)
-    del rows
-    r.set_viewport(WIDTH, HEIGHT)
-    r.set_blend_mode(L.BLEND_UNORM8 if args.blend == "unorm8" else L.BLEND_FP32)
+    if not (world == 1 and not args.no_cpu_baseline and args.config == "c2"):
+        del rows
+    r.set_viewport(W_, H_)
     # a side stream: the legacy default stream's handle is 0, which the C ABI reads as "the renderer's own stream"
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     assert sptr != 0
-    # the orbit's views are dealt round-robin: at step i rank g renders view i * world + g (neighbours on the orbit)
-    cams = [vkgs_b200.camera_block(*view_camera(i * world + rank)) for i in range(max(K, W))]
-    img_bytes = WIDTH * HEIGHT * 4
-    GATHER_EVERY, NBUF = 4, 2
-    # finished images go to rank 0 in batches of GATHER_EVERY frames; the gather of one batch (NCCL, its own stream)
-    # overlaps the rendering of the next into the other buffer
-    batches = [torch.empty((GATHER_EVERY, HEIGHT, WIDTH, 4), dtype=torch.uint8, device=dev) for _ in range(NBUF)]
-    gathered = [[torch.empty_like(batches[0]) for _ in range(world)] if (world > 1 and rank == 0) else None
-                for _ in range(NBUF)]
-    pending = [None] * NBUF
-
-    def drain():
-        for b in range(NBUF):
-            if pending[b] is not None:
-                pending[b].wait()
-                pending[b] = None
-
-    def frame_device(i):
-        b, j = (i // GATHER_EVERY) % NBUF, i % GATHER_EVERY
-        if j == 0 and pending[b] is not None:   # the buffer's previous gather must have read it
-            pending[b].wait()
-            pending[b] = None
-        r.set_camera(block=cams[i % len(cams)])
-        r.draw_device(dst_ptr=batches[b][j].data_ptr(), stream=sptr)
-        if world > 1 and j == GATHER_EVERY - 1:
-            pending[b] = dist.gather(batches[b], gathered[b], dst=0, async_op=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput (`value`)
+    if args.config == "c5":
+        line = run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stream, barrier)
+    else:
+        line = run_views(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stream, barrier)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline and args.config == "c2":
+            fps, secs, desc, cores = cpu_sample(cfg, rows)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                                    "frame_ms_estimate": 1e3 / fps, "sample_seconds": secs}
+        print(json.dumps(line))
+    r.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_views(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stream, barrier):
+    """c2 / c4: views sharded across ranks, finished images delivered to rank 0."""
+    import vkgs_b200
+    K, W = args.steps, args.warmup
+    W_, H_ = cfg["width"], cfg["height"]
+    sptr = stream.cuda_stream
+    img_bytes = W_ * H_ * 4
+    if args.config == "c4":
+        # strong scaling of one 360-view orbit: rank g renders its contiguous block of the views (dist.shard_views);
+        # --steps bounds the views per rank so that a default run stays short
+        mine = list(vdist.shard_views(cfg["n_views"], rank, world))
+        K = min(K, len(mine))
+        views = [mine[i % len(mine)] for i in range(max(K, W))]
+        total_views = sum(min(args.steps, len(vdist.shard_views(cfg["n_views"], g, world))) for g in range(world))
+    else:
+        # weak scaling: K frames per rank; rank g's block of the orbit starts at view g * K (contiguous blocks, the way
+        # dist.shard_views deals them)
+        views = [rank * K + i for i in range(max(K, W))]
+        total_views = world * K
+    cams = [vkgs_b200.camera_block(*view_camera(cfg, v)) for v in views]
+    if world > 1 and args.gather == "peer":
+        slots = max(K, W) if max(K, W) * world * img_bytes <= (24 << 30) else max(8, (24 << 30) // (world * img_bytes))
+        deliver = PeerWrite(torch, dist, dev, world, rank, H_, W_, local, slots)
+    else:
+        deliver = NcclGather(torch, dist, dev, world, rank, H_, W_)
+
+    def frame_device(i):
+        r.set_camera(block=cams[i % len(cams)])
+        r.draw_device(dst_ptr=deliver.dst(i), stream=sptr)
+        deliver.sent(i)
+
+    def timed(mode):
+        r.set_blend_mode(mode)
+        for i in range(W):
+            frame_device(i)
+        deliver.drain()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        for i in range(W):   # the GPU stays under load while the sampler comes up
+            frame_device(i)
+        deliver.drain()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sampler.mark_begin()
+        e0.record(stream)
+        for i in range(K):
+            frame_device(i)
+        deliver.drain()   # every image has arrived on rank 0 inside the timed region (peer writes: when the stream
+        e1.record(stream)  # and the barrier below have completed)
+        barrier()
+        sampler.mark_end()
+        ms = vdist.max_over_ranks(e0.elapsed_time(e1), dev)
+        return ms, sampler.stop()
+
+    # ---- end to end through the public API with host buffers: camera blocks in, pixels out to pinned host memory,
+    #      in orbit batches of E2E_BATCH views per vkgsb_draw_batch call (frame i crosses PCIe while frame i+1 renders;
+    #      the call returns when every image of the batch is in host memory)
+    host = torch.empty((E2E_BATCH, H_, W_, 4), dtype=torch.uint8).pin_memory()
+
+    def e2e(mode):
+        r.set_blend_mode(mode)
+
+        def frames(k):
+            done = 0
+            while done < k:
+                nb = min(E2E_BATCH, k - done)
+                r.draw_batch_to_host_ptr([cams[(done + j) % len(cams)] for j in range(nb)], host.data_ptr(), stream=sptr)
+                done += nb
+        frames(E2E_BATCH)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        frames(K)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = vdist.max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)), dev)  # device and host clocks
+        return ms, int(host[0].sum().item())
+
+    # ---- per-stage times (eager launches with events between stages) and the fragments the blend stage shades
+    def stages(mode):
+        r.set_blend_mode(mode)
+        r.set_option(L.OPT_STAGE_TIMING, 1)
+        acc = dict(ms_project=0.0, ms_sort=0.0, ms_bin=0.0, ms_blend=0.0, ms_total=0.0)
+        vis, pairs, totals, retries = [], [], [], []
+        for i in range(W + K):
+            r.set_camera(block=cams[i % len(cams)])
+            r.draw_device(stream=sptr)
+            if i >= W:
+                s = r.stats()
+                for k in acc:
+                    acc[k] += s[k]
+                vis.append(s["visible_point_count"]); pairs.append(s["pair_count"]); totals.append(s["ms_total"])
+                retries.append(s["blend_retries"])
+        r.set_option(L.OPT_COUNT_FRAGMENTS, 1)
+        frags = []
+        for i in range(min(K, len(cams), 64)):
+            r.set_camera(block=cams[i])
+            r.draw_device(stream=sptr)
+            frags.append(r.stats()["fragment_count"])
+        r.set_option(L.OPT_COUNT_FRAGMENTS, 0)
+        r.set_option(L.OPT_STAGE_TIMING, 0)
+        st = {k[3:]: v / K for k, v in acc.items()}
+        return dict(stages=st, V=float(np.mean(vis)), D=float(np.mean(pairs)), totals=totals, overflow=int(r.stats()["pair_overflow"]),
+                    fragments=float(np.mean(frags)), retries=float(np.mean(retries)))
+
+    FP32, U8 = L.BLEND_FP32, L.BLEND_UNORM8
+    head, other = (FP32, U8) if args.blend == "fp32" else (U8, FP32)
+    ms, clocks = timed(head)
+    ms_o, clocks_o = timed(other) if args.config == "c2" else (None, None)
+    e2e_ms, checksum = e2e(head)
+    e2e_ms_o, _ = e2e(other) if args.config == "c2" else (None, None)
+    S = stages(head)
+    S_o = stages(other) if args.config == "c2" else None
+    r.set_blend_mode(head)
+    if hasattr(deliver, "close"):
+        barrier()
+        deliver.close()
+    if rank != 0:
+        return None
+
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    stage, V_mean = S["stages"], S["V"]
+    alg_bytes = 12.0 * cfg["n_splats"] + 180.0 * V_mean            # SURVEY.md §8(d): reference-layout algorithmic bytes
+    proj_gbs = alg_bytes / (stage["project"] * 1e-3) / 1e9
+    dominant = max(("project", "sort", "bin", "blend"), key=lambda k: stage[k])
+    traffic, traffic_src = ncu_traffic()
+    frag_ceiling = 148 * 128 * sm_mhz * 1e6 / FP32_INSTR_PER_FRAGMENT     # SURVEY.md 8(d): FP32 lanes / 20 instructions
+
+    def blend_block(S_):
+        fps_ = S_["fragments"] / (S_["stages"]["blend"] * 1e-3)
+        return {"fragments_per_frame": S_["fragments"], "fragments_per_s": fps_,
+                "fp32_issue_frac": fps_ / frag_ceiling, "fp32_instr_per_fragment_assumed": FP32_INSTR_PER_FRAGMENT,
+                "smem_bytes_per_entry": SMEM_BYTES_PER_ENTRY, "retries_per_frame": S_["retries"]}
+
+    name = {FP32: "fp32", U8: "unorm8"}
+    total = total_views if args.config == "c4" else world * K
+    line = {
+        "metric": cfg["metric"], "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "blend": name[head], "visible_mean": V_mean, "pairs_mean": S["D"],
+                   "parallelism": (f"views sharded over {world} GPU(s) in contiguous blocks, scene replicated, " + deliver.name)
+                   if world > 1 else "single GPU",
+                   "l2": f"inputs larger than L2: {144 * cfg['n_splats'] / 1e6:.0f} MB resident scene streamed per frame, "
+                         "a different camera each step",
+                   "pair_overflow": S["overflow"]},
+        "stages_ms": stage,
+        # per-frame device time over the orbit (the views differ in cost): SURVEY.md 8(d) asks for the spread
+        "frame_ms": {"p10": float(np.percentile(S["totals"], 10)), "p50": float(np.percentile(S["totals"], 50)),
+                     "p90": float(np.percentile(S["totals"], 90))},
+        "sort_gkeys_per_s": V_mean / (stage["sort"] * 1e-3) / 1e9,
+        "sort_hbm_frac": 68.0 * V_mean / (stage["sort"] * 1e-3) / 1e9 / hbm_peak,
+        "roofline": {"kernel": "k_cull + k_project (the projection stage)", "bound": "hbm", "achieved": proj_gbs,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": proj_gbs / hbm_peak, "traffic": traffic,
+                     "traffic_source": traffic_src, "peak_kind": peak_kind, "algorithmic_bytes": alg_bytes,
+                     "share_of_step": stage["project"] / stage["total"], "dominant_by_time": dominant},
+        "blend": blend_block(S),
+        "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": PARAM_BYTES, "batch": E2E_BATCH,
+                "d2h_bytes_per_step": img_bytes + 24, "checksum": checksum},
+        "gpu_launches": KERNELS_PER_FRAME * K,
+        "clocks": clocks,
+    }
+    if S_o is not None:
+        o = name[other]
+        line[f"value_{o}"] = total / (ms_o * 1e-3)
+        line[f"ms_per_step_{o}"] = ms_o / K
+        line[f"stages_ms_{o}"] = S_o["stages"]
+        line[f"blend_{o}"] = blend_block(S_o)
+        line[f"e2e_{o}"] = {"value": total / (e2e_ms_o * 1e-3), "unit": UNIT}
+        line[f"clocks_{o}"] = clocks_o
+    return line
+
+
+def run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stream, barrier):
+    """c5: ONE frame per step, rank g renders band g (rows balanced on the per-row histogram of splat centres), the
+    bands land in rank 0's frame.  value = assembled frames/s; strong scaling against the same frame on one GPU."""
+    import vkgs_b200
+    K, W = args.steps, args.warmup
+    K = min(K, 40)
+    W_, H_ = cfg["width"], cfg["height"]
+    sptr = stream.cuda_stream
+    cams = [vkgs_b200.camera_block(*view_camera(cfg, v)) for v in range(cfg["n_views"])]
+    r.set_blend_mode(L.BLEND_UNORM8 if args.blend == "unorm8" else L.BLEND_FP32)
+    if world > 1:
+        # band edges balanced on the splat centres per row, summed over one whole frame per view of the orbit (every rank
+        # holds the scene and computes the same edges).  One set of edges for the whole run: a band is part of the
+        # recorded frame graph.
+        hist = np.zeros(H_, np.float64)
+        for cam in cams:
+            r.set_camera(block=cam)
+            r.draw_device()
+            r.sync()
+            hist += r.row_histogram()
+        edges = vdist.balanced_band_edges(hist, world)
+    else:
+        edges = [0, H_]
+    img_bytes = W_ * H_ * 4
+    if world > 1 and args.gather == "peer":
+        deliver = PeerWrite(torch, dist, dev, 1, 0 if rank == 0 else 1, H_, W_, local, 2)   # ONE frame per slot: every rank writes its rows of it
+        deliver.rank, deliver.world = 0, 1
+    else:
+        deliver = None
+        frame = torch.zeros((H_, W_, 4), dtype=torch.uint8, device=dev)
+        gathered = [torch.empty_like(frame) for _ in range(world)] if (world > 1 and rank == 0) else None
+    r.set_band(edges[rank], edges[rank + 1]) if world > 1 else r.set_band(0, 0)
+
+    def step(i):
+        r.set_camera(block=cams[i % len(cams)])
+        if deliver is not None:
+            # every rank's blend kernel writes its band's rows straight into rank 0's frame (slot i & 1); the ranks meet
+            # before a slot is reused
+            if i >= 2:
+                dist.barrier()
+            r.draw_device(dst_ptr=deliver.base + (i & 1) * img_bytes, stream=sptr)
+        else:
+            r.draw_device(dst_ptr=frame.data_ptr(), stream=sptr)
+            if world > 1:
+                dist.gather(frame, gathered, dst=0)
+
     for i in range(W):
-        frame_device(i)
-    drain()
+        step(i)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    for i in range(W):   # the GPU stays under load while the sampler comes up
-        frame_device(i)
-    drain()
+    for i in range(W):
+        step(i)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.mark_begin()
     e0.record(stream)
     for i in range(K):
-        frame_device(i)
-    drain()   # every gathered image has arrived on rank 0 inside the timed region
+        step(i)
     e1.record(stream)
     barrier()
     sampler.mark_end()
     ms = vdist.max_over_ranks(e0.elapsed_time(e1), dev)
     clocks = sampler.stop()
-    st = r.stats()
-
-    # ---- end to end through the public API with host buffers (`e2e`): camera blocks in, pixels out to pinned host
-    #      memory, in orbit batches of E2E_BATCH views per vkgsb_draw_batch call (the C4 usage pattern: frame i crosses
-    #      PCIe while frame i+1 renders; the call returns when every image of the batch is in host memory)
-    host = torch.empty((E2E_BATCH, HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory()
-
-    def e2e_frames(k0, k):
-        done = 0
-        while done < k:
-            nb = min(E2E_BATCH, k - done)
-            r.draw_batch_to_host_ptr([cams[(k0 + done + j) % len(cams)] for j in range(nb)], host.data_ptr(), stream=sptr)
-            done += nb
-
-    e2e_frames(0, E2E_BATCH)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    e2e_frames(0, K)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    e2e_ms = vdist.max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)), dev)  # device and host clocks
-    checksum = int(host[0].sum().item())
-
-    # ---- per-stage times (eager launches with events between stages)
     r.set_option(L.OPT_STAGE_TIMING, 1)
-    acc = dict(ms_project=0.0, ms_sort=0.0, ms_bin=0.0, ms_blend=0.0, ms_total=0.0)
-    vis, pairs, totals = [], [], []
-    for i in range(W + K):
+    acc, vis = {}, []
+    for i in range(3 + 8):
         r.set_camera(block=cams[i % len(cams)])
         r.draw_device(stream=sptr)
-        if i >= W:
+        if i >= 3:
             s = r.stats()
-            for k in acc:
-                acc[k] += s[k]
-            vis.append(s["visible_point_count"]); pairs.append(s["pair_count"]); totals.append(s["ms_total"])
+            for k in ("ms_project", "ms_sort", "ms_bin", "ms_blend", "ms_total"):
+                acc[k[3:]] = acc.get(k[3:], 0.0) + s[k] / 8
+            vis.append(s["visible_point_count"])
     r.set_option(L.OPT_STAGE_TIMING, 0)
-    stage = {k: v / K for k, v in acc.items()}
-    V_mean, D_mean = float(np.mean(vis)), float(np.mean(pairs))
-
-    peaks, peak_kind = measured_peaks()
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = 12.0 * N_SPLATS + 180.0 * V_mean            # reference-layout algorithmic bytes
-    proj_gbs = alg_bytes / (stage["ms_project"] * 1e-3) / 1e9
-    sort_gkeys = V_mean / (stage["ms_sort"] * 1e-3) / 1e9
-    dominant = max(("ms_project", "ms_sort", "ms_bin", "ms_blend"), key=lambda k: stage[k])
-    traffic, traffic_src = ncu_traffic()
-
-    if rank == 0:
-        fps = world * K / (ms * 1e-3)
-        line = {
-            "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "blend": args.blend, "visible_mean": V_mean, "pairs_mean": D_mean,
-                       "parallelism": f"views sharded over {world} GPU(s), scene replicated, images gathered to rank 0 (NCCL)"
-                       if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: 834 MB resident scene streamed per frame, a different camera each step",
-                       "pair_overflow": int(st["pair_overflow"])},
-            "stages_ms": {"project": stage["ms_project"], "sort": stage["ms_sort"], "bin": stage["ms_bin"],
-                          "blend": stage["ms_blend"], "total": stage["ms_total"]},
-            # per-frame device time over the orbit (the views differ in cost): SURVEY.md 8(d) asks for the spread
-            "frame_ms": {"p10": float(np.percentile(totals, 10)), "p50": float(np.percentile(totals, 50)),
-                         "p90": float(np.percentile(totals, 90))},
-            "sort_gkeys_per_s": sort_gkeys,
-            "sort_hbm_frac": 68.0 * V_mean / (stage["ms_sort"] * 1e-3) / 1e9 / hbm_peak,
-            "roofline": {"kernel": "k_project", "bound": "hbm", "achieved": proj_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": proj_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_kind": peak_kind,
-                         "algorithmic_bytes": alg_bytes, "share_of_step": stage["ms_project"] / stage["ms_total"],
-                         "dominant_by_time": dominant.replace("ms_", "")},
-            "e2e": {"value": world * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": PARAM_BYTES, "batch": E2E_BATCH,
-                    "d2h_bytes_per_step": img_bytes + 12, "checksum": checksum},
-            "gpu_launches": KERNELS_PER_FRAME * K,
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_sample(lambda: synth.scene_bicycle(N_SPLATS))
-            line["cpu_baseline"] = cb
-        print(json.dumps(line))
-    r.close()
-    if world > 1:
-        dist.destroy_process_group()
+    slowest = vdist.max_over_ranks(acc["total"], dev)
+    if deliver is not None:
+        barrier()
+        deliver.rank = 0 if rank == 0 else 1
+        deliver.close()
+    if rank != 0:
+        return None
+    return {
+        "metric": cfg["metric"], "value": K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": cfg["workload"], "blend": args.blend, "band_edges": edges,
+                   "parallelism": (f"{world} screen bands on {world} GPU(s), scene replicated, band edges balanced on the row "
+                                   "histogram; " + (PeerWrite.name if deliver is not None else "bands gathered to rank 0 (NCCL)"))
+                   if world > 1 else "single GPU, whole frame",
+                   "l2": f"inputs larger than L2: {144 * cfg['n_splats'] / 1e6:.0f} MB resident scene streamed per frame",
+                   "rank0_visible_mean": float(np.mean(vis))},
+        "stages_ms": acc, "slowest_band_stages_ms_total": slowest,
+        "gpu_launches": KERNELS_PER_FRAME * K, "clocks": clocks,
+    }
 
 
 if __name__ == "__main__":

@@ -47,7 +47,8 @@ enum vkgsb_status {
 enum vkgsb_blend_mode {
   VKGSB_BLEND_FP32 = 0,  /* fp32 accumulation, one UNORM8 quantisation at the end; front-to-back with early exit */
   VKGSB_BLEND_UNORM8 = 1 /* the reference's render target (render_pass.cc:15): destination re-quantised to
-                            UNORM8 after every splat, back-to-front, no early exit */
+                            UNORM8 after every splat, back-to-front; the walk starts where the splats in front already
+                            hide everything behind, certified per pixel to within 1/255 of the full walk */
 };
 
 enum vkgsb_pixel_format {
@@ -88,9 +89,11 @@ typedef struct vkgsb_stats {
   float ms_blend;               /* splat.vert/.frag + ROP equivalent */
   float ms_total;
   uint64_t frame_counter;
-  uint32_t blend_full_walks;    /* VKGSB_BLEND_UNORM8: warps (16x8 pixels) whose late-start bracket stayed open and that
-                                   walked their whole list instead (exact either way; a cost indicator) */
+  uint32_t blend_retries;       /* VKGSB_BLEND_UNORM8: warp (16x8 pixels) attempts whose late-start bracket was still more
+                                   than 1 level wide at the front and that started again from deeper (a cost indicator) */
   uint32_t pad0;
+  uint64_t fragment_count;      /* fragments (pixel x splat pairs inside the +-3 sigma quad) the blend stage shaded in the
+                                   last frame; only counted while VKGSB_OPT_COUNT_FRAGMENTS is on */
 } vkgsb_stats;
 
 enum vkgsb_option {
@@ -102,10 +105,15 @@ enum vkgsb_option {
   VKGSB_OPT_BAND_Y1 = 4,      /* 0 => full height */
   VKGSB_OPT_KEEP_INSTANCES = 5, /* 1: also store the reference-format instance records (projection.comp:177-179) so
                                   vkgsb_read_instances can return them; off by default (48 B/visible splat of writes) */
-  VKGSB_OPT_BAND_CULL = 6     /* default 1: while a band is set, splats whose footprint provably cannot reach it are
+  VKGSB_OPT_BAND_CULL = 6,    /* default 1: while a band is set, splats whose footprint provably cannot reach it are
                                  dropped at the cull, so sort, projection and binning shrink with the band; the visible
                                  count and the parity taps then describe the band's subset (same relative order).
                                  0: cull on the centre alone, as the full frame does (rank.comp:37) */
+  VKGSB_OPT_COUNT_FRAGMENTS = 7, /* 1: the blend stage also counts the fragments it shades (vkgsb_stats.fragment_count): the
+                                 stage's work unit for fragments/s figures; costs a few percent, off by default */
+  VKGSB_OPT_UNORM8_CUT_EXP = 8 /* k in [1, 18], default 5: VKGSB_BLEND_UNORM8 starts its back-to-front walk where the
+                                 transmittance of the splats in front is below 10^-k (deeper = fewer retries, longer
+                                 walks); the result is certified either way */
 };
 
 VKGSB_API const char* vkgsb_last_error(void);

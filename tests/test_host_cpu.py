@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert C.sizeof(L.CameraBlock) == (16 + 16 + 4 + 16) * 4
     assert C.sizeof(L.Config) == 32
-    assert C.sizeof(L.Stats) == 64
+    assert C.sizeof(L.Stats) == 72
 
 
 def test_no_device_is_a_loud_error():

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("VKGSB_LIB") or os.path.join(_HERE, "lib", "libvkgsb.s
 OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_CAPACITY, ERR_NO_SCENE, ERR_CANCELLED = range(7)
 BLEND_FP32, BLEND_UNORM8 = 0, 1
 FORMAT_RGBA8, FORMAT_BGRA8 = 0, 1
-OPT_STAGE_TIMING, OPT_BLEND_MODE, OPT_PIXEL_FORMAT, OPT_BAND_Y0, OPT_BAND_Y1, OPT_KEEP_INSTANCES, OPT_BAND_CULL = range(7)
+OPT_STAGE_TIMING, OPT_BLEND_MODE, OPT_PIXEL_FORMAT, OPT_BAND_Y0, OPT_BAND_Y1, OPT_KEEP_INSTANCES, OPT_BAND_CULL, OPT_COUNT_FRAGMENTS, OPT_UNORM8_CUT_EXP = range(9)
 
 
 class Config(C.Structure):
@@ -29,8 +29,8 @@ class Stats(C.Structure):
     _fields_ = [("total_point_count", C.c_uint32), ("loaded_point_count", C.c_uint32),
                 ("visible_point_count", C.c_uint32), ("pair_overflow", C.c_uint32), ("pair_count", C.c_uint64),
                 ("ms_project", C.c_float), ("ms_sort", C.c_float), ("ms_bin", C.c_float), ("ms_blend", C.c_float),
-                ("ms_total", C.c_float), ("frame_counter", C.c_uint64), ("blend_full_walks", C.c_uint32),
-                ("pad0", C.c_uint32)]
+                ("ms_total", C.c_float), ("frame_counter", C.c_uint64), ("blend_retries", C.c_uint32),
+                ("pad0", C.c_uint32), ("fragment_count", C.c_uint64)]
 
 
 # every entry point include/vkgsb.h declares: name -> (restype, argtypes)

@@ -18,15 +18,18 @@
 //                    A <- a*a + A*(1-a), A0 = 1); one UNORM8 rounding at the end.
 // VKGSB_BLEND_UNORM8 the reference's target semantics: back-to-front, destination re-quantised after every splat like an
 //                    8-bit ROP, q <- rint(fma(255*src, a, q*(1-a))).  The recurrence cannot stop early, but it can
-//                    START late, exactly: every step q -> rint(fma(s, a, q*(1-a))) is monotone non-decreasing in q
-//                    (a in [0,1]), so a whole run of splats F satisfies F(0) <= F(q) <= F(255) for every possible
-//                    destination value q.  A front-to-back pre-pass (transmittance only) finds per pixel the list
-//                    position where T < 1e-4; the back-to-front walk starts THERE with the bracket lo = 0, hi = 255 in
-//                    every channel and runs both ends through the same recurrence.  Where the ends meet (they do after
-//                    a few opaque splats; from then on one state is carried) the result is what the full walk over
-//                    everything behind would have produced, bit for bit, whatever that is.  A warp in which some
-//                    pixel's ends have NOT met at the front of the list repeats the walk over the entire list
-//                    (counted in Control::blend_full_walks): exact always, fast where splats are opaque.
+//                    START late, with a certificate: every step is monotone non-decreasing in q (a in [0,1]), so a run
+//                    of splats F satisfies F(0) <= F(q) <= F(255) for every possible destination value q, and a step
+//                    never widens a gap (F(q+g) - F(q) <= g).  Phase A (front to back, transmittance only) finds per
+//                    pixel the list position where T < tau; phase B walks back to front from THERE with the bracket
+//                    lo = 0, hi = 255 in every channel, both ends through the exact recurrence, until the ends are at
+//                    most 1 apart in every channel of the warp's 128 pixels (a few opaque splats), then carries lo
+//                    alone.  At the front lo is then within 1/255 of what the full walk over everything behind would
+//                    have produced - equal to it wherever the ends met - whatever lies behind.  A warp whose ends are
+//                    still further apart (faint layers keep an 8-bit destination 'stuck', tests/
+//                    test_unorm8_bracket_cpu.py) tries again with tau^2 (Control::blend_retries), finally from the far
+//                    end of the list, where the start value is the background: always certified, fast where splats
+//                    are opaque.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -81,7 +84,9 @@ __device__ __forceinline__ uint32_t subtile_mask(uint32_t x0, uint32_t x1, uint3
 // LAYER: an opaque line layer lies under the splats (lines.cu; the reference's axis / grid, engine.cc:1440-1469).  A
 // fragment is kept only if the splat's ndc.z is LESS than the layer's depth at the pixel (engine.cc:298-299), and the
 // result is composited over the layer's colour instead of the clear colour.
-template <int MODE, bool LAYER, int ROWS>
+// COUNT: also count the fragments shaded (pixel x splat pairs inside the +-3 sigma square that reach the blend
+// arithmetic) into Control::fragment_count - the work unit of this stage; off on the timed path.
+template <int MODE, bool LAYER, int ROWS, bool COUNT>
 __global__ void __launch_bounds__(128 * ROWS, MODE == VKGSB_BLEND_FP32_MODE ? 1024 / (128 * ROWS) : 1)
 k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const uint2* __restrict__ ranges,
         const uint32_t* __restrict__ pair_rank, const float4* __restrict__ rrec, int bgra, uint32_t reg_y0,
@@ -93,7 +98,7 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
   float4* s_q2 = s_q1 + kBatch;
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_q2 + kBatch);
   float* s_z = reinterpret_cast<float*>(s_mask + kBatch);  // LAYER only
-  __shared__ uint32_t s_alive, s_redo;
+  __shared__ uint32_t s_alive, s_redo, s_from;
 
   const uint32_t width = fpp->width, bins_x = fpp->bins_x;
   const uint32_t band_y0 = fpp->band_y0, band_y1 = fpp->band_y1;
@@ -159,12 +164,14 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
     e.z = LAYER ? s_z[j] : 0.f;
     return e;
   };
+  uint32_t nfrag = 0;
   // alpha of entry e at pixel k of this lane; false when the pixel is outside the +-3 sigma square / behind the layer
   auto fragment = [&](const Entry& e, int k, float* al) {
     const float px = fmaf(e.q0.x, flx, fmaf(e.q0.y, fly[k], e.bx));
     const float py = fmaf(e.q0.z, flx, fmaf(e.q0.w, fly[k], e.by));
     if (!(fabsf(px) <= 3.f && fabsf(py) <= 3.f && (!LAYER || e.z < ldepth[k]))) return false;
     *al = __saturatef(e.q2.y * __expf(-0.5f * fmaf(py, py, px * px)));
+    if (COUNT) ++nfrag;
     return true;
   };
   uint32_t* img = reinterpret_cast<uint32_t*>(image);
@@ -232,92 +239,119 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
             pack_pixel(quantize8(cr[k]), quantize8(cg[k]), quantize8(cb[k]), quantize8(ca[k] + T[k]), bgra);
       }
   } else {
-    // ---- phase A, front to back: transmittance only.  cut[k] = list position of the splat that took pixel k below
-    //      the transmittance cut (kNoCut: never - the pixel's walk starts at the far end, from the real background)
+    // State of a pixel across attempts: its transmittance so far (phase A resumes where it stopped) and the list
+    // position of the splat that took it below the current cut (kNoCut: not reached - the walk of that pixel starts at
+    // the far end of the list, from the real background, and is exact).
+    float T[kPix];
     uint32_t cut[kPix];
-    uint32_t last_b0 = range.x;  // the last batch phase A staged (CTA-uniform)
-    {
-      float T[kPix];
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) {
+      T[k] = 1.f;
+      cut[k] = kNoCut;
+    }
+    const bool any_inside = __any_sync(0xffffffffu, inside[0] || inside[1] || inside[2] || inside[3]);
+    bool wfinal = !any_inside || range.y == range.x;  // warp-uniform: this warp's pixels are written
+    uint32_t wnext = range.x;                         // warp-uniform: first list position phase A has not examined
+    uint32_t last_b0 = range.x;                       // CTA-uniform: the deepest batch phase A has staged
+    float tau = fpp->unorm8_cut;
+    if (range.y == range.x) {  // nothing in the list: the background
+#pragma unroll
+      for (int k = 0; k < kPix; ++k)
+        if (inside[k]) img[static_cast<size_t>(y_first + 2 * k) * width + x] =
+            pack_pixel(lrgba[k] & 255u, (lrgba[k] >> 8) & 255u, (lrgba[k] >> 16) & 255u, 255u, bgra);
+    }
+    if (tid == 0) {
+      s_alive = 0u;
+      s_redo = 0u;
+      s_from = range.y;
+    }
+    __syncthreads();
+    if (!wfinal && lane == 0) atomicOr(&s_redo, wbit);  // s_redo = the warps still working
+    __syncthreads();
+    for (uint32_t attempt = 0; s_redo != 0u; ++attempt) {
+      // ---- phase A, front to back, transmittance only, resumed: until every pixel of every working warp is below
+      //      tau (or the list ends)
       bool done[kPix];
 #pragma unroll
       for (int k = 0; k < kPix; ++k) {
-        T[k] = 1.f;
-        done[k] = !inside[k];
-        cut[k] = kNoCut;
+        done[k] = !inside[k] || T[k] < tau;
+        if (!done[k]) cut[k] = kNoCut;  // set again when it crosses this attempt's (lower) tau
       }
-      bool warp_done = __all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3]);
-      if (tid == 0) {
-        s_alive = 0xffffffffu >> (32 - 4 * ROWS);
-        s_redo = 0u;
+      bool warp_done = wfinal || wnext >= range.y || __all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3]);
+      if (!warp_done && lane == 0) {
+        atomicOr(&s_alive, wbit);
+        atomicMin(&s_from, wnext);
       }
       __syncthreads();
-      if (warp_done && lane == 0) atomicAnd(&s_alive, ~wbit);
-      __syncthreads();
-      for (uint32_t b0 = range.x; b0 < range.y; b0 += kBatch) {
-        const uint32_t alive = s_alive;
-        if (alive == 0u) break;
-        last_b0 = b0;
-        const uint32_t cnt = min(static_cast<uint32_t>(kBatch), range.y - b0);
-        stage(b0, cnt, alive);
-        __syncthreads();
-        if (!warp_done) {
-          for (uint32_t g0 = 0; g0 < cnt && !warp_done; g0 += 32) {
-            const uint32_t m = (g0 + lane < cnt) ? s_mask[g0 + lane] : 0u;
-            uint32_t bits = __ballot_sync(0xffffffffu, (m & wbit) != 0u);
-            while (bits) {
-              const uint32_t j = g0 + __ffs(bits) - 1;
-              bits &= bits - 1;
-              const Entry e = entry(j);
+      if (s_alive != 0u) {
+        for (uint32_t b0 = range.x + ((s_from - range.x) / kBatch) * kBatch; b0 < range.y; b0 += kBatch) {
+          const uint32_t alive = s_alive;
+          if (alive == 0u) break;
+          last_b0 = max(last_b0, b0);
+          const uint32_t cnt = min(static_cast<uint32_t>(kBatch), range.y - b0);
+          stage(b0, cnt, alive);
+          __syncthreads();
+          if (!warp_done) {
+            for (uint32_t g0 = 0; g0 < cnt && !warp_done; g0 += 32) {
+              const uint32_t gi = b0 + g0 + lane;
+              const uint32_t m = (g0 + lane < cnt && gi >= wnext) ? s_mask[g0 + lane] : 0u;
+              uint32_t bits = __ballot_sync(0xffffffffu, (m & wbit) != 0u);
+              while (bits) {
+                const uint32_t j = g0 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const Entry e = entry(j);
 #pragma unroll
-              for (int k = 0; k < kPix; ++k) {
-                float al;
-                if (!done[k] && fragment(e, k, &al)) {
-                  T[k] = __fmul_rn(T[k], __fsub_rn(1.f, al));
-                  if (T[k] < kTransmittanceCut) {
-                    done[k] = true;
-                    cut[k] = b0 + j;
+                for (int k = 0; k < kPix; ++k) {
+                  float al;
+                  if (!done[k] && fragment(e, k, &al)) {
+                    T[k] = __fmul_rn(T[k], __fsub_rn(1.f, al));
+                    if (T[k] < tau) {
+                      done[k] = true;
+                      cut[k] = b0 + j;
+                    }
                   }
                 }
-              }
-              if (__all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3])) {
-                warp_done = true;
-                if (lane == 0) atomicAnd(&s_alive, ~wbit);
-                break;
+                if (__all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3])) {
+                  warp_done = true;
+                  wnext = b0 + j + 1;
+                  if (lane == 0) atomicAnd(&s_alive, ~wbit);
+                  break;
+                }
               }
             }
+            if (!warp_done) wnext = b0 + cnt;
           }
+          __syncthreads();
         }
-        __syncthreads();
       }
-    }
-    // ---- phase B, back to front from the cuts: both ends of the bracket through the exact recurrence
-    float lo[kPix][4], hi[kPix][4];
+      // ---- phase B, back to front from the cuts: both ends of the bracket through the exact recurrence
+      float lo[kPix][4], hi[kPix][4];
 #pragma unroll
-    for (int k = 0; k < kPix; ++k) {
-      const bool open = cut[k] != kNoCut;
-      lo[k][0] = open ? 0.f : static_cast<float>(lrgba[k] & 255u);
-      lo[k][1] = open ? 0.f : static_cast<float>((lrgba[k] >> 8) & 255u);
-      lo[k][2] = open ? 0.f : static_cast<float>((lrgba[k] >> 16) & 255u);
-      lo[k][3] = open ? 0.f : 255.f;
-      hi[k][0] = open ? 255.f : lo[k][0];
-      hi[k][1] = open ? 255.f : lo[k][1];
-      hi[k][2] = open ? 255.f : lo[k][2];
-      hi[k][3] = 255.f;
-      if (!inside[k]) cut[k] = 0u;  // never drawn
-    }
-    auto walk = [&](uint32_t from_b0, bool whole_list) {
+      for (int k = 0; k < kPix; ++k) {
+        const bool open = cut[k] != kNoCut;
+        lo[k][0] = open ? 0.f : static_cast<float>(lrgba[k] & 255u);
+        lo[k][1] = open ? 0.f : static_cast<float>((lrgba[k] >> 8) & 255u);
+        lo[k][2] = open ? 0.f : static_cast<float>((lrgba[k] >> 16) & 255u);
+        lo[k][3] = open ? 0.f : 255.f;
+        hi[k][0] = open ? 255.f : lo[k][0];
+        hi[k][1] = open ? 255.f : lo[k][1];
+        hi[k][2] = open ? 255.f : lo[k][2];
+        hi[k][3] = 255.f;
+      }
       // the warp's deepest start; entries behind it are skipped without a look
       uint32_t wcut = 0;
 #pragma unroll
-      for (int k = 0; k < kPix; ++k) wcut = max(wcut, whole_list ? (inside[k] ? kNoCut : 0u) : cut[k]);
+      for (int k = 0; k < kPix; ++k) wcut = max(wcut, inside[k] ? cut[k] : 0u);
       wcut = __reduce_max_sync(0xffffffffu, wcut);
-      bool met = whole_list;  // warp-uniform: every pixel's ends have met - one state is enough from here on
-      for (uint32_t b0 = from_b0;; b0 -= kBatch) {
+      // warp-uniform: in every channel of every pixel the ends are at most 1 apart.  A ROP step never widens the gap
+      // (|F(q + g) - F(q)| <= g for 0 <= a <= 1), so from here on one end is enough: the other stays within 1 of it.
+      bool met = false;
+      for (uint32_t b0 = last_b0;; b0 -= kBatch) {
         const uint32_t cnt = min(static_cast<uint32_t>(kBatch), range.y - b0);
         __syncthreads();  // the previous batch has been consumed
-        stage(b0, cnt, 0xffffffffu);
+        stage(b0, cnt, s_redo);
         __syncthreads();
-        if ((!whole_list || (s_redo & wbit)) && wcut >= b0) {
+        if (!wfinal && wcut >= b0) {
           for (int g0 = static_cast<int>((cnt - 1) & ~31u); g0 >= 0; g0 -= 32) {
             const uint32_t gi = b0 + g0 + lane;
             const uint32_t m = (g0 + lane < cnt && gi <= wcut) ? s_mask[g0 + lane] : 0u;
@@ -327,28 +361,27 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
               const uint32_t j = g0 + top;
               bits &= ~(1u << top);
               const Entry e = entry(j);
-              const float s255[4] = {__fmul_rn(255.f, e.q1.z), __fmul_rn(255.f, e.q1.w), __fmul_rn(255.f, e.q2.x), 0.f};
+              const float s255[3] = {__fmul_rn(255.f, e.q1.z), __fmul_rn(255.f, e.q1.w), __fmul_rn(255.f, e.q2.x)};
               if (!met) {
 #pragma unroll
                 for (int k = 0; k < kPix; ++k) {
                   float al;
-                  if ((whole_list || b0 + j <= cut[k]) && fragment(e, k, &al)) {
+                  if (b0 + j <= cut[k] && fragment(e, k, &al)) {
                     const float om = __fsub_rn(1.f, al), a255 = __fmul_rn(255.f, al);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                      const float s = c < 3 ? s255[c] : a255;
-                      lo[k][c] = rint255(fmaf(s, al, __fmul_rn(lo[k][c], om)));
-                      hi[k][c] = rint255(fmaf(s, al, __fmul_rn(hi[k][c], om)));
+                      const float sc = c < 3 ? s255[c < 3 ? c : 0] : a255;
+                      lo[k][c] = rint255(fmaf(sc, al, __fmul_rn(lo[k][c], om)));
+                      hi[k][c] = rint255(fmaf(sc, al, __fmul_rn(hi[k][c], om)));
                     }
                   }
                 }
-                bool same = true;
+                bool close = true;  // a pixel still waiting for its (nearer) cut holds 0 / 255: not close
 #pragma unroll
                 for (int k = 0; k < kPix; ++k)
 #pragma unroll
-                  for (int c = 0; c < 4; ++c) same = same && lo[k][c] == hi[k][c];
-                // once met, always met; a pixel still waiting for its (nearer) cut holds 0 / 255: not met
-                met = __all_sync(0xffffffffu, same);
+                  for (int c = 0; c < 4; ++c) close = close && (!inside[k] || hi[k][c] - lo[k][c] <= 1.f);
+                met = __all_sync(0xffffffffu, close);
               } else {
 #pragma unroll
                 for (int k = 0; k < kPix; ++k) {
@@ -357,8 +390,8 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
                     const float om = __fsub_rn(1.f, al), a255 = __fmul_rn(255.f, al);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                      const float s = c < 3 ? s255[c] : a255;
-                      lo[k][c] = rint255(fmaf(s, al, __fmul_rn(lo[k][c], om)));
+                      const float sc = c < 3 ? s255[c < 3 ? c : 0] : a255;
+                      lo[k][c] = rint255(fmaf(sc, al, __fmul_rn(lo[k][c], om)));
                     }
                   }
                 }
@@ -368,46 +401,46 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
         }
         if (b0 == range.x) break;
       }
-      if (met) {
+      // ---- the certificate: ends at most 1 apart everywhere -> lo is within 1/255 of the exact recurrence's result
+      //      (equal to it where the ends met).  Otherwise the warp tries again from a deeper cut.
+      if (!wfinal) {
+        bool close = true;
+        if (!met) {
 #pragma unroll
-        for (int k = 0; k < kPix; ++k)
+          for (int k = 0; k < kPix; ++k)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) hi[k][c] = lo[k][c];
-      }
-    };
-    if (range.y > range.x) {
-      walk(last_b0, false);
-      bool bad = false;
-#pragma unroll
-      for (int k = 0; k < kPix; ++k)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) bad = bad || (inside[k] && lo[k][c] != hi[k][c]);
-      if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_redo, wbit);
-      __syncthreads();
-      // ---- phase C (rare): a bracket stayed open at the front of the list -> the exact full walk for that warp
-      if (s_redo != 0u) {
-        if (s_redo & wbit) {
-#pragma unroll
-          for (int k = 0; k < kPix; ++k) {
-            lo[k][0] = hi[k][0] = static_cast<float>(lrgba[k] & 255u);
-            lo[k][1] = hi[k][1] = static_cast<float>((lrgba[k] >> 8) & 255u);
-            lo[k][2] = hi[k][2] = static_cast<float>((lrgba[k] >> 16) & 255u);
-            lo[k][3] = hi[k][3] = 255.f;
-          }
-          if (lane == 0) atomicAdd(&ctrl->blend_full_walks, 1u);
+            for (int c = 0; c < 4; ++c) close = close && (!inside[k] || hi[k][c] - lo[k][c] <= 1.f);
+          close = __all_sync(0xffffffffu, close);
         }
-        walk(range.x + ((range.y - 1 - range.x) / kBatch) * kBatch, true);
-      }
-    }
+        if (close) {
 #pragma unroll
-    for (int k = 0; k < kPix; ++k)
-      if (inside[k])
-        img[static_cast<size_t>(y_first + 2 * k) * width + x] =
-            pack_pixel(clamp255(lo[k][0]), clamp255(lo[k][1]), clamp255(lo[k][2]), clamp255(lo[k][3]), bgra);
+          for (int k = 0; k < kPix; ++k)
+            if (inside[k])
+              img[static_cast<size_t>(y_first + 2 * k) * width + x] =
+                  pack_pixel(clamp255(lo[k][0]), clamp255(lo[k][1]), clamp255(lo[k][2]), clamp255(lo[k][3]), bgra);
+          wfinal = true;
+        } else if (lane == 0) {
+          atomicAdd(&ctrl->blend_retries, 1u);
+        }
+      }
+      __syncthreads();  // everyone has read s_redo (staging) before it changes
+      if (tid == 0) {
+        s_alive = 0u;
+        s_from = range.y;
+      }
+      if (wfinal && lane == 0) atomicAnd(&s_redo, ~wbit);
+      // 1e-5 -> 1e-10 -> 1e-20 -> 0 (never reached: every cut opens at the far end, where the start value is known)
+      tau = attempt >= 2 ? 0.f : tau * tau;
+      __syncthreads();
+    }
+  }
+  if (COUNT) {
+    nfrag = __reduce_add_sync(0xffffffffu, nfrag);
+    if (lane == 0 && nfrag) atomicAdd(&ctrl->fragment_count, static_cast<unsigned long long>(nfrag));
   }
 }
 
-template <int MODE, bool LAYER, int ROWS>
+template <int MODE, bool LAYER, int ROWS, bool COUNT>
 static void blend_launch(const FrameParams* d_fp, const FrameParams& h_fp, Control* d_ctrl, const uint2* d_ranges,
                          const uint32_t* d_pair_rank, const float4* rrec, int bgra, const unsigned long long* d_layer,
                          const float* d_zndc, uint8_t* d_image, cudaStream_t stream) {
@@ -416,33 +449,46 @@ static void blend_launch(const FrameParams* d_fp, const FrameParams& h_fp, Contr
   const uint32_t ry0 = h_fp.band_y0 / RH, ry1 = (h_fp.band_y1 + RH - 1) / RH;
   const uint32_t nreg = h_fp.bins_x * (ry1 - ry0);
   if (nreg == 0) return;
-  k_blend<MODE, LAYER, ROWS><<<nreg, 128 * ROWS, blend_smem(LAYER), stream>>>(d_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra,
-                                                                            ry0, d_layer, d_zndc, d_image);
+  k_blend<MODE, LAYER, ROWS, COUNT><<<nreg, 128 * ROWS, blend_smem(LAYER), stream>>>(d_fp, d_ctrl, d_ranges, d_pair_rank, rrec,
+                                                                                   bgra, ry0, d_layer, d_zndc, d_image);
 }
 
-void blend_configure() {
-  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_FP32_MODE, false, kRowsFp32>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(false));
-  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_UNORM8_MODE, false, kRowsUnorm8>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(false));
-  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_FP32_MODE, true, kRowsFp32>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(true));
-  cudaFuncSetAttribute(k_blend<VKGSB_BLEND_UNORM8_MODE, true, kRowsUnorm8>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(true));
+template <int MODE, int ROWS>
+static void blend_opt_in() {
+  cudaFuncSetAttribute(k_blend<MODE, false, ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(false));
+  cudaFuncSetAttribute(k_blend<MODE, false, ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(false));
+  cudaFuncSetAttribute(k_blend<MODE, true, ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(true));
+  cudaFuncSetAttribute(k_blend<MODE, true, ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, blend_smem(true));
+}
+void blend_configure() {  // once per device: opt in to > 48 KB dynamic shared memory
+  blend_opt_in<VKGSB_BLEND_FP32_MODE, kRowsFp32>();
+  blend_opt_in<VKGSB_BLEND_UNORM8_MODE, kRowsUnorm8>();
+}
+
+template <int MODE, int ROWS>
+static void blend_dispatch(const FrameParams* d_fp, const FrameParams& h_fp, Control* d_ctrl, const uint2* d_ranges,
+                           const uint32_t* d_pair_rank, const float4* rrec, int bgra, bool count,
+                           const unsigned long long* d_layer, const float* d_zndc, uint8_t* d_image, cudaStream_t stream) {
+  const bool layer = d_layer != nullptr && d_zndc != nullptr;
+  if (layer) {
+    if (count) blend_launch<MODE, true, ROWS, true>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, d_layer, d_zndc, d_image, stream);
+    else blend_launch<MODE, true, ROWS, false>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, d_layer, d_zndc, d_image, stream);
+  } else {
+    if (count) blend_launch<MODE, false, ROWS, true>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, nullptr, nullptr, d_image, stream);
+    else blend_launch<MODE, false, ROWS, false>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, nullptr, nullptr, d_image, stream);
+  }
 }
 
 void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, Control* d_ctrl, const uint2* d_ranges,
-                  const uint32_t* d_pair_rank, const float* d_rrec, int blend_mode, int bgra,
+                  const uint32_t* d_pair_rank, const float* d_rrec, int blend_mode, int bgra, bool count_fragments,
                   const unsigned long long* d_layer, const float* d_zndc, uint8_t* d_image, cudaStream_t stream) {
   const float4* rrec = reinterpret_cast<const float4*>(d_rrec);
-  const bool layer = d_layer != nullptr && d_zndc != nullptr;
-  if (blend_mode == VKGSB_BLEND_FP32_MODE) {
-    if (layer)
-      blend_launch<VKGSB_BLEND_FP32_MODE, true, kRowsFp32>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, d_layer, d_zndc, d_image, stream);
-    else
-      blend_launch<VKGSB_BLEND_FP32_MODE, false, kRowsFp32>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, nullptr, nullptr, d_image, stream);
-  } else {
-    if (layer)
-      blend_launch<VKGSB_BLEND_UNORM8_MODE, true, kRowsUnorm8>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, d_layer, d_zndc, d_image, stream);
-    else
-      blend_launch<VKGSB_BLEND_UNORM8_MODE, false, kRowsUnorm8>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, nullptr, nullptr, d_image, stream);
-  }
+  if (blend_mode == VKGSB_BLEND_FP32_MODE)
+    blend_dispatch<VKGSB_BLEND_FP32_MODE, kRowsFp32>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, count_fragments,
+                                                     d_layer, d_zndc, d_image, stream);
+  else
+    blend_dispatch<VKGSB_BLEND_UNORM8_MODE, kRowsUnorm8>(d_fp, h_fp, d_ctrl, d_ranges, d_pair_rank, rrec, bgra, count_fragments,
+                                                         d_layer, d_zndc, d_image, stream);
 }
 
 }  // namespace vkgsb

@@ -71,7 +71,7 @@ struct FrameParams {
   // band cull (kFlagBandCull): the footprint's pixel half-height ey satisfies
   //   ey^2 <= bc_a * (bc_p + x_ndc^2 + y_ndc^2) * lambda_max(Sigma) / w^2 + bc_b
   float bc_a, bc_b, bc_p;
-  float pad3;
+  float unorm8_cut;  // VKGSB_BLEND_UNORM8: transmittance below which the first attempt starts its back-to-front walk
 };
 
 // ---- control block: everything the host zeroes with one memset per frame --------------------------------------
@@ -79,12 +79,13 @@ struct Control {
   uint32_t visible_count;   // V  (VisiblePointCount, rank.comp:38)
   uint32_t pair_count;      // D
   uint32_t pair_overflow;
-  uint32_t blend_full_walks; // UNORM8 blend: warps whose bracket stayed open and walked their whole list (blend.cu)
+  uint32_t blend_retries;    // UNORM8 blend: warp attempts whose bracket stayed open at the front (blend.cu)
+  unsigned long long fragment_count;  // fragments shaded by the blend stage (VKGSB_OPT_COUNT_FRAGMENTS)
   uint32_t tile_cut;        // binning tiles [0, tile_cut) fit in max_pairs (bin.cu)
   uint32_t partial_pairs;   // pairs kept of the last kept tile when the capacity cut falls inside it
   uint32_t bin_items;       // work items of k_bin_count / k_bin_place
   uint32_t sort_ticket[4];  // depth passes
-  uint32_t pad[1];
+  uint32_t pad[3];
   uint32_t hist_depth[4 * 256];
 };
 

@@ -98,7 +98,7 @@ void launch_lines(const FrameParams* d_fp, uint32_t n_lines, const float* d_pos,
 // d_ranges: [begin,end) of every coarse bin in d_pair_slot
 // d_layer / d_zndc: both null, or the line layer and the splats' ndc.z by slot (depth test LESS against the layer)
 void launch_blend(const FrameParams* d_fp, const FrameParams& h_fp, Control* d_ctrl, const uint2* d_ranges,
-                  const uint32_t* d_pair_slot, const float* d_rrec, int blend_mode, int bgra,
+                  const uint32_t* d_pair_slot, const float* d_rrec, int blend_mode, int bgra, bool count_fragments,
                   const unsigned long long* d_layer, const float* d_zndc, uint8_t* d_image, cudaStream_t stream);
 
 // ---- misc ----------------------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 // dispatch (engine.cc:1218-1219, projection.comp:64-75).
 #include <atomic>
 #include <condition_variable>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -94,6 +95,8 @@ struct vkgsb_renderer {
   bool have_cam = false;
   uint32_t width = 0, height = 0;
   int blend_mode = VKGSB_BLEND_FP32, pixel_format = VKGSB_FORMAT_RGBA8, stage_timing = 0, keep_instances = 0;
+  int count_fragments = 0;
+  float unorm8_cut = 1e-5f;
   bool last_frame_has_instances = false;
   uint32_t band_y0 = 0, band_y1 = 0;
   int band_cull = 1;  // VKGSB_OPT_BAND_CULL
@@ -321,7 +324,7 @@ void fill_params(vkgsb_renderer* r) {
     p.bc_a = static_cast<float>(9.0 * hh * hh * w2);
     p.bc_b = 9.f * hh * hh * (p.lpx + p.lpy);
     p.bc_p = P[0] * P[0] + P[5] * P[5];
-    p.pad3 = 0.f;
+    p.unorm8_cut = r->unorm8_cut;
     if (shaped && banded && r->band_cull) p.flags |= kFlagBandCull;
   }
 }
@@ -356,10 +359,10 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   launch_bin(r->d_fp, r->h_fp.ncbins, r->ctrl, r->slots, r->bin_rect, n, r->max_pairs, r->bin, r->ranges, r->bin_slots, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[3], s));
   launch_blend(r->d_fp, r->h_fp, r->ctrl, r->ranges, r->bin_slots, r->rrec, r->blend_mode,
-               r->pixel_format == VKGSB_FORMAT_BGRA8, r->n_lines ? r->layer : nullptr, r->n_lines ? r->zndc : nullptr,
+               r->pixel_format == VKGSB_FORMAT_BGRA8, r->count_fragments != 0, r->n_lines ? r->layer : nullptr, r->n_lines ? r->zndc : nullptr,
                r->image, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[4], s));
-  CU_TRY(cudaMemcpyAsync(r->h_counts, r->ctrl, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(r->h_counts, r->ctrl, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaGetLastError());
   return VKGSB_OK;
 }
@@ -560,6 +563,11 @@ int vkgsb_set_option(vkgsb_renderer* r, int option, int64_t value) {
     case VKGSB_OPT_BAND_Y0: r->band_y0 = static_cast<uint32_t>(value); break;
     case VKGSB_OPT_BAND_Y1: r->band_y1 = static_cast<uint32_t>(value); break;
     case VKGSB_OPT_BAND_CULL: r->band_cull = value != 0; break;
+    case VKGSB_OPT_COUNT_FRAGMENTS: r->count_fragments = value != 0; break;
+    case VKGSB_OPT_UNORM8_CUT_EXP:
+      if (value < 1 || value > 18) return fail(VKGSB_ERR_INVALID, "unorm8 cut exponent must be in [1, 18]");
+      r->unorm8_cut = std::pow(10.f, -static_cast<float>(value));
+      break;
     default: return fail(VKGSB_ERR_INVALID, "unknown option");
   }
   invalidate_graph(r);
@@ -749,7 +757,8 @@ int vkgsb_get_stats(vkgsb_renderer* r, vkgsb_stats* out) {
   out->visible_point_count = r->h_counts[0];
   out->pair_count = r->h_counts[1];
   out->pair_overflow = r->h_counts[2];
-  out->blend_full_walks = r->h_counts[3];
+  out->blend_retries = r->h_counts[3];
+  out->fragment_count = static_cast<uint64_t>(r->h_counts[4]) | (static_cast<uint64_t>(r->h_counts[5]) << 32);
   out->frame_counter = r->frame_counter;
   if (r->ev_recorded) {
     CU_TRY(cudaEventElapsedTime(&out->ms_project, r->ev[0], r->ev[1]));
