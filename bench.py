@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 UNIT = "frames/s"
-PARAM_BYTES = 548                 # sizeof(FrameParams): the per-frame host->device upload (a kernel argument)
+PARAM_BYTES = 560                 # sizeof(FrameParams): the per-frame host->device upload (a kernel argument)
 E2E_BATCH = 8                     # views per vkgsb_draw_batch call in the end-to-end leg
 SMEM_BYTES_PER_ENTRY = 52         # blend stage: 3 x float4 raster record + 4-byte sub-tile mask per staged list entry
 FP32_INSTR_PER_FRAGMENT = 20      # algorithmic FP32 instructions per fragment (the blend roofline's unit)
@@ -356,6 +356,10 @@ def main():
     if not (world == 1 and not args.no_cpu_baseline and args.config == "c2"):
         del rows
     r.set_viewport(W_, H_)
+    if os.environ.get("VKGSB_L2_PIN_MB"):          # experiments: how much of the splat centres is kept in L2
+        r.set_option(L.OPT_L2_PIN_MB, int(os.environ["VKGSB_L2_PIN_MB"]))
+    if os.environ.get("VKGSB_UNORM8_CUT_EXP"):
+        r.set_option(L.OPT_UNORM8_CUT_EXP, int(os.environ["VKGSB_UNORM8_CUT_EXP"]))
     # a side stream: the legacy default stream's handle is 0, which the C ABI reads as "the renderer's own stream"
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)

@@ -111,9 +111,12 @@ enum vkgsb_option {
                                  0: cull on the centre alone, as the full frame does (rank.comp:37) */
   VKGSB_OPT_COUNT_FRAGMENTS = 7, /* 1: the blend stage also counts the fragments it shades (vkgsb_stats.fragment_count): the
                                  stage's work unit for fragments/s figures; costs a few percent, off by default */
-  VKGSB_OPT_UNORM8_CUT_EXP = 8 /* k in [1, 18], default 5: VKGSB_BLEND_UNORM8 starts its back-to-front walk where the
+  VKGSB_OPT_UNORM8_CUT_EXP = 8, /* k in [1, 18], default 4: VKGSB_BLEND_UNORM8 starts its back-to-front walk where the
                                  transmittance of the splats in front is below 10^-k (deeper = fewer retries, longer
                                  walks); the result is certified either way */
+  VKGSB_OPT_L2_PIN_MB = 9     /* default 72: the centres (12 B/splat) of the first that-many MB of splats are kept in the
+                                 126 MB L2 across frames (evict_last), so the cull stream of a scene of up to ~6 M splats
+                                 is an L2 hit from the second frame on; 0 disables */
 };
 
 VKGSB_API const char* vkgsb_last_error(void);
@@ -159,7 +162,9 @@ VKGSB_API int vkgsb_row_histogram(vkgsb_renderer* r, uint32_t* rows, uint32_t ca
 /* One frame: rank -> sort -> projection -> draw (engine.cc:1164-1290), into an RGBA8/BGRA8 image of
  * width*height*4 bytes.  dst may be NULL (image stays in the renderer, see vkgsb_image_device_ptr), a host pointer
  * (dst_is_device = 0: device->host copy, returns when the pixels are in dst) or a device pointer (dst_is_device = 1:
- * asynchronous on `stream`).  stream = a cudaStream_t cast to void*, NULL = the renderer's own stream. */
+ * asynchronous on `stream`; the blend stage writes its pixels straight into dst - no copy - and while a band is set
+ * only the band's rows of dst are written).  dst may live on another GPU of the node (vkgsb_shared_open): the pixel
+ * stores then travel over NVLink.  stream = a cudaStream_t cast to void*, NULL = the renderer's own stream. */
 VKGSB_API int vkgsb_draw(vkgsb_renderer* r, void* dst, int dst_is_device, void* stream);
 /* n_views frames with one scene: cameras[i] -> dst + i*stride bytes (same dst rules). */
 VKGSB_API int vkgsb_draw_batch(vkgsb_renderer* r, uint32_t n_views, const vkgsb_camera* cameras, void* dst,
@@ -167,6 +172,20 @@ VKGSB_API int vkgsb_draw_batch(vkgsb_renderer* r, uint32_t n_views, const vkgsb_
 VKGSB_API int vkgsb_image_device_ptr(vkgsb_renderer* r, void** ptr);
 VKGSB_API int vkgsb_sync(vkgsb_renderer* r);
 VKGSB_API int vkgsb_get_stats(vkgsb_renderer* r, vkgsb_stats* out);
+
+/* Destinations shared between the processes of one node (one process per GPU): the consumer process
+ * allocates a device buffer and exports a 64-byte handle (CUDA IPC); each producer process maps it and passes
+ * mapped pointer + offset as vkgsb_draw's device destination, so a finished view - or one screen band's rows of a
+ * frame - lands in the consumer GPU's memory without a copy kernel, a staging buffer or a collective.  The reference is
+ * single-GPU (context.cc:94-132); its interop pattern for handing images to another API is external memory by file
+ * descriptor (interop/cuda_image.cu:77-132).  Ordering is the caller's: a producer's frame is complete when its stream
+ * is, and processes meet with whatever barrier they already have. */
+VKGSB_API int vkgsb_shared_create(int device, size_t bytes, void** d_ptr, uint8_t handle[64]);
+VKGSB_API int vkgsb_shared_open(int device, const uint8_t handle[64], void** d_ptr);
+VKGSB_API int vkgsb_shared_close(int device, void* d_ptr);
+/* consumer side without a CUDA runtime of its own: bytes [offset, offset + bytes) of the buffer -> host memory */
+VKGSB_API int vkgsb_shared_read(int device, const void* d_ptr, size_t offset, size_t bytes, void* host_dst);
+VKGSB_API int vkgsb_shared_destroy(int device, void* d_ptr);
 
 /* Parity taps (test / debugging): state of the last drawn frame, copied to host.
  * read_sorted: keys/ids in sorted (far -> near) order = SplatStorage.key / .index after vrdx (engine.cc:1218-1219).

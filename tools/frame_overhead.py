@@ -14,12 +14,12 @@ import vkgs_b200  # noqa: E402
 from vkgs_b200 import synth  # noqa: E402
 
 view = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-rows = synth.scene_bicycle(bench.N_SPLATS)
-r = vkgs_b200.Renderer(device=0, max_splats=bench.N_SPLATS, max_width=bench.WIDTH, max_height=bench.HEIGHT, max_pairs=64_000_000)
+rows = synth.scene_bicycle(bench.CONFIGS["c2"]["n_splats"])
+r = vkgs_b200.Renderer(device=0, max_splats=bench.CONFIGS["c2"]["n_splats"], max_width=bench.CONFIGS["c2"]["width"], max_height=bench.CONFIGS["c2"]["height"], max_pairs=64_000_000)
 r.upload_splats(rows)
 del rows
-r.set_viewport(bench.WIDTH, bench.HEIGHT)
-cam = vkgs_b200.camera_block(*bench.view_camera(view))
+r.set_viewport(bench.CONFIGS["c2"]["width"], bench.CONFIGS["c2"]["height"])
+cam = vkgs_b200.camera_block(*bench.view_camera(bench.CONFIGS["c2"], view))
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -43,9 +43,10 @@ def main():
             except OSError:
                 pass
     if args.config == "c2":
-        n, w, h = bench.N_SPLATS, bench.WIDTH, bench.HEIGHT
+        cfg = bench.CONFIGS["c2"]
+        n, w, h = cfg["n_splats"], cfg["width"], cfg["height"]
         rows = synth.scene_bicycle(n)
-        cam = vkgs_b200.camera_block(*bench.view_camera(args.view))
+        cam = vkgs_b200.camera_block(*bench.view_camera(cfg, args.view))
     else:
         from vkgs_b200 import camera as pycam
         n, w, h = 5_834_734, 1920, 1080

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("VKGSB_LIB") or os.path.join(_HERE, "lib", "libvkgsb.s
 OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_CAPACITY, ERR_NO_SCENE, ERR_CANCELLED = range(7)
 BLEND_FP32, BLEND_UNORM8 = 0, 1
 FORMAT_RGBA8, FORMAT_BGRA8 = 0, 1
-OPT_STAGE_TIMING, OPT_BLEND_MODE, OPT_PIXEL_FORMAT, OPT_BAND_Y0, OPT_BAND_Y1, OPT_KEEP_INSTANCES, OPT_BAND_CULL, OPT_COUNT_FRAGMENTS, OPT_UNORM8_CUT_EXP = range(9)
+OPT_STAGE_TIMING, OPT_BLEND_MODE, OPT_PIXEL_FORMAT, OPT_BAND_Y0, OPT_BAND_Y1, OPT_KEEP_INSTANCES, OPT_BAND_CULL, OPT_COUNT_FRAGMENTS, OPT_UNORM8_CUT_EXP, OPT_L2_PIN_MB = range(10)
 
 
 class Config(C.Structure):
@@ -62,6 +62,11 @@ SIGNATURES = {
     "vkgsb_read_scene": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "vkgsb_sort_storage_bytes": (C.c_int, [C.c_uint32, C.POINTER(C.c_size_t)]),
     "vkgsb_sort_key_value_indirect": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
+    "vkgsb_shared_create": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P), _P]),
+    "vkgsb_shared_open": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "vkgsb_shared_close": (C.c_int, [C.c_int, _P]),
+    "vkgsb_shared_read": (C.c_int, [C.c_int, _P, C.c_size_t, C.c_size_t, _P]),
+    "vkgsb_shared_destroy": (C.c_int, [C.c_int, _P]),
     "vkgsb_camera_orbit": (C.c_int, [C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, _P,
                                      C.POINTER(CameraBlock)]),
 }

@@ -174,7 +174,8 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
     if (COUNT) ++nfrag;
     return true;
   };
-  uint32_t* img = reinterpret_cast<uint32_t*>(image);
+  // the frame's destination travels in the parameter block, so one recorded graph serves every destination
+  uint32_t* img = reinterpret_cast<uint32_t*>(fpp->dst_image ? reinterpret_cast<uint8_t*>(fpp->dst_image) : image);
 
   if (MODE == VKGSB_BLEND_FP32_MODE) {
     float T[kPix], cr[kPix], cg[kPix], cb[kPix], ca[kPix];
@@ -429,7 +430,7 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
         s_from = range.y;
       }
       if (wfinal && lane == 0) atomicAnd(&s_redo, ~wbit);
-      // 1e-5 -> 1e-10 -> 1e-20 -> 0 (never reached: every cut opens at the far end, where the start value is known)
+      // tau -> tau^2 -> tau^4 -> 0 (never reached: every cut opens at the far end, where the start value is known)
       tau = attempt >= 2 ? 0.f : tau * tau;
       __syncthreads();
     }

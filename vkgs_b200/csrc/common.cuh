@@ -66,13 +66,18 @@ struct FrameParams {
   uint32_t cbins_x;             // coarse bins per row
   uint32_t cbin_y0;             // first coarse row of the band
   uint32_t ncbins;              // coarse bins covering the band: cbins_x * rows (<= kMaxCoarseBins)
-  uint32_t pad1[3];
+  uint32_t l2_pin_splats;       // centres of splats [0, l2_pin_splats) are kept in L2 across frames (project.cu)
+  uint32_t pad1[2];
   float pvm_lines[16];          // (proj*view)*model of the line layer (color.vert, engine.cc:1444-1448)
   // band cull (kFlagBandCull): the footprint's pixel half-height ey satisfies
   //   ey^2 <= bc_a * (bc_p + x_ndc^2 + y_ndc^2) * lambda_max(Sigma) / w^2 + bc_b
   float bc_a, bc_b, bc_p;
   float unorm8_cut;  // VKGSB_BLEND_UNORM8: transmittance below which the first attempt starts its back-to-front walk
+  uint32_t pad4;
+  unsigned long long dst_image;  // where the blend stage writes this frame's pixels: the renderer's own image, or the
+                                 // caller's device destination (possibly another GPU's memory, mapped over NVLink)
 };
+static_assert(sizeof(FrameParams) % 8 == 0, "FrameParams carries a 64-bit pointer");
 
 // ---- control block: everything the host zeroes with one memset per frame --------------------------------------
 struct Control {

@@ -45,8 +45,9 @@ void project_configure();  // once per device: opt in to > 48 KB dynamic shared 
 // when FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control and writes
 // Control::visible_count.
 void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl, const CullIndex& ix, uint32_t* d_keys,
-                    uint32_t* d_slots, uint32_t* d_vis_id, float* d_rrec, uint32_t* d_bin_rect, float* d_inst,
-                    float* d_zndc, cudaStream_t stream);
+                    float* d_rrec, uint32_t* d_bin_rect, float* d_inst, float* d_zndc, cudaStream_t stream);
+// parity taps: splat id of every visible slot of the last frame (from its cull index) -> d_vis_id
+void launch_expand_ids(const CullIndex& ix, uint32_t n, uint32_t* d_vis_id, cudaStream_t stream);
 
 // ---- sort.cu: onesweep LSD radix sort, count read on the device ----------------------------------------------------
 struct SortArgs {
@@ -66,6 +67,7 @@ struct SortArgs {
   int npass;                // 1 .. 4
   uint8_t bits[4];          // digit width per pass: 8 (0 reads as 8: the reference's digit) or 9; sum of 2^bits <= 1024
   bool values_only;         // the caller only reads the sorted values: the last pass does not store keys
+  bool vals_identity;       // the values are 0, 1, 2, ...: the first pass generates them instead of reading `vals`
   uint32_t clustered_passes;  // bit p: pass p's digit takes only a handful of values (ranked with match.any, one round
                               // per distinct value, instead of one ballot per bit)
 };

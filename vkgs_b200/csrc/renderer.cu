@@ -96,7 +96,8 @@ struct vkgsb_renderer {
   uint32_t width = 0, height = 0;
   int blend_mode = VKGSB_BLEND_FP32, pixel_format = VKGSB_FORMAT_RGBA8, stage_timing = 0, keep_instances = 0;
   int count_fragments = 0;
-  float unorm8_cut = 1e-5f;
+  float unorm8_cut = 1e-4f;
+  int l2_pin_mb = 72;  // VKGSB_OPT_L2_PIN_MB
   bool last_frame_has_instances = false;
   uint32_t band_y0 = 0, band_y1 = 0;
   int band_cull = 1;  // VKGSB_OPT_BAND_CULL
@@ -290,7 +291,8 @@ void fill_params(vkgsb_renderer* r) {
     if (p.cshift_x <= p.cshift_y) ++p.cshift_x; else ++p.cshift_y;
   }
   p.ncbins = p.cbins_x * crows;
-  p.pad1[0] = p.pad1[1] = p.pad1[2] = 0u;
+  p.pad1[0] = p.pad1[1] = 0u;
+  p.l2_pin_splats = static_cast<uint32_t>(std::min<uint64_t>(r->scene_n.load(), (static_cast<uint64_t>(r->l2_pin_mb) << 20) / 12u));
   // Band rendering (one GPU of a screen-band partition): splats whose footprint cannot reach the band
   // are dropped at the cull, so sort / projection / binning shrink with the band.  The footprint's pixel box has
   // half-height ey = 3 * (H/2) * (|RS10| + |RS11|) <= 3 * (H/2) * sqrt(trace(cov2d))   (RS RS^T = cov2d), and
@@ -339,7 +341,7 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   if (r->n_lines) launch_lines(r->d_fp, r->n_lines, r->line_pos, r->line_col, r->width, r->height, r->layer, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[0], s));
   // the depth sort runs an odd number of passes: its input goes to the ping-pong side, its result lands in keys / slots
-  launch_project(sc, r->d_fp, r->ctrl, r->cull, r->keys_alt, r->slots_alt, r->vis_id, r->rrec, r->bin_rect, r->inst,
+  launch_project(sc, r->d_fp, r->ctrl, r->cull, r->keys_alt, r->rrec, r->bin_rect, r->inst,
                  r->n_lines ? r->zndc : nullptr, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
   SortArgs depth{};
@@ -354,6 +356,7 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   depth.bits[0] = 8; depth.bits[1] = 8; depth.bits[2] = 9;
   depth.clustered_passes = 1u << 2;  // bits 16..24 of (1 - z) * 2^24: a few values per warp
   depth.have_hist = true;  // k_project accumulated the three digit histograms
+  depth.vals_identity = true;  // the value is the compacted slot: generated by the first pass
   launch_sort(depth, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[2], s));
   launch_bin(r->d_fp, r->h_fp.ncbins, r->ctrl, r->slots, r->bin_rect, n, r->max_pairs, r->bin, r->ranges, r->bin_slots, s);
@@ -367,12 +370,15 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   return VKGSB_OK;
 }
 
-int run_frame(vkgsb_renderer* r, cudaStream_t s) {
+// `direct_dst`: a device destination the blend stage writes straight into (null: the renderer's own image)
+int run_frame(vkgsb_renderer* r, cudaStream_t s, void* direct_dst = nullptr) {
   if (!r->have_cam) return fail(VKGSB_ERR_INVALID, "vkgsb_set_camera has not been called");
   if (r->width == 0 || r->height == 0) return fail(VKGSB_ERR_INVALID, "vkgsb_set_viewport has not been called");
   const uint32_t n = r->scene_n.load();
   if (n == 0) return fail(VKGSB_ERR_NO_SCENE, "no splats loaded");
   fill_params(r);
+  r->h_fp.pad4 = 0u;
+  r->h_fp.dst_image = reinterpret_cast<unsigned long long>(direct_dst);
   k_set_params<<<1, 32, 0, s>>>(r->h_fp, r->d_fp);
   if (r->stage_timing) {
     if (int e = record_stages(r, s, true)) return e;
@@ -564,6 +570,10 @@ int vkgsb_set_option(vkgsb_renderer* r, int option, int64_t value) {
     case VKGSB_OPT_BAND_Y1: r->band_y1 = static_cast<uint32_t>(value); break;
     case VKGSB_OPT_BAND_CULL: r->band_cull = value != 0; break;
     case VKGSB_OPT_COUNT_FRAGMENTS: r->count_fragments = value != 0; break;
+    case VKGSB_OPT_L2_PIN_MB:
+      if (value < 0 || value > 4096) return fail(VKGSB_ERR_INVALID, "L2 pin size out of range");
+      r->l2_pin_mb = static_cast<int>(value);
+      break;
     case VKGSB_OPT_UNORM8_CUT_EXP:
       if (value < 1 || value > 18) return fail(VKGSB_ERR_INVALID, "unorm8 cut exponent must be in [1, 18]");
       r->unorm8_cut = std::pow(10.f, -static_cast<float>(value));
@@ -683,11 +693,12 @@ int vkgsb_draw(vkgsb_renderer* r, void* dst, int dst_is_device, void* stream) {
   if (set_device(r)) return VKGSB_ERR_CUDA;
   std::lock_guard<std::mutex> g(r->draw_mutex);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : r->stream;
-  if (int e = run_frame(r, s)) return e;
+  // a device destination is rendered into directly (no copy): the blend kernel's stores go to `dst`, wherever it lives
+  if (int e = run_frame(r, s, dst && dst_is_device ? dst : nullptr)) return e;
   const size_t bytes = static_cast<size_t>(r->width) * r->height * 4;
-  if (dst) {
-    CU_TRY(cudaMemcpyAsync(dst, r->image, bytes, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
-    if (!dst_is_device) CU_TRY(cudaStreamSynchronize(s));
+  if (dst && !dst_is_device) {
+    CU_TRY(cudaMemcpyAsync(dst, r->image, bytes, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
   }
   return VKGSB_OK;
 }
@@ -726,9 +737,7 @@ int vkgsb_draw_batch(vkgsb_renderer* r, uint32_t n_views, const vkgsb_camera* ca
   for (uint32_t i = 0; i < n_views; ++i) {
     r->cam = cameras[i];
     r->have_cam = true;
-    if (int e = run_frame(r, s)) return e;
-    if (dst)
-      CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + i * dst_stride, r->image, bytes, cudaMemcpyDeviceToDevice, s));
+    if (int e = run_frame(r, s, dst ? static_cast<uint8_t*>(dst) + i * dst_stride : nullptr)) return e;
   }
   return VKGSB_OK;
 }
@@ -790,7 +799,8 @@ int vkgsb_read_sorted(vkgsb_renderer* r, uint32_t* keys, uint32_t* ids, uint32_t
     }
   }
   if (ids) {
-    // slots_alt is free between frames: gather ids there
+    // slots_alt is free between frames: gather ids there; the ids by slot come from the frame's cull index
+    launch_expand_ids(r->cull, r->scene_n.load(), r->vis_id, r->stream);
     launch_gather_sorted(r->ctrl, r->slots, r->vis_id, r->inst, v, r->slots_alt, nullptr, r->stream);
     CU_TRY(cudaStreamSynchronize(r->stream));
     CU_TRY(cudaMemcpy(ids, r->slots_alt, v * 4ull, cudaMemcpyDeviceToHost));
@@ -861,6 +871,55 @@ int vkgsb_read_scene(vkgsb_renderer* r, float* pos, float* cov, float* opacity, 
   if (sh && e == cudaSuccess) e = cudaMemcpy(sh, ds, n * 96ull, cudaMemcpyDeviceToHost);
   cudaFree(dp); cudaFree(dc); cudaFree(dop); cudaFree(ds);
   CU_TRY(e);
+  return VKGSB_OK;
+}
+
+// ---- cross-process destinations on one node --------------------------------------------------------------
+int vkgsb_shared_create(int device, size_t bytes, void** d_ptr, uint8_t handle[64]) {
+  if (!d_ptr || !handle || bytes == 0) return fail(VKGSB_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  CU_TRY(cudaSetDevice(device));
+  void* p = nullptr;
+  CU_TRY(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(VKGSB_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  std::memcpy(handle, &h, 64);
+  *d_ptr = p;
+  return VKGSB_OK;
+}
+
+int vkgsb_shared_open(int device, const uint8_t handle[64], void** d_ptr) {
+  if (!d_ptr || !handle) return fail(VKGSB_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  CU_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return VKGSB_OK;
+}
+
+int vkgsb_shared_close(int device, void* d_ptr) {
+  if (!d_ptr) return VKGSB_OK;
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaIpcCloseMemHandle(d_ptr));
+  return VKGSB_OK;
+}
+
+int vkgsb_shared_read(int device, const void* d_ptr, size_t offset, size_t bytes, void* host_dst) {
+  if (!d_ptr || !host_dst) return fail(VKGSB_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaMemcpy(host_dst, static_cast<const uint8_t*>(d_ptr) + offset, bytes, cudaMemcpyDeviceToHost));
+  return VKGSB_OK;
+}
+
+int vkgsb_shared_destroy(int device, void* d_ptr) {
+  if (!d_ptr) return VKGSB_OK;
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaFree(d_ptr));
   return VKGSB_OK;
 }
 

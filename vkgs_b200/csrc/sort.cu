@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kSortThreads, 4) k_sort_onesweep(SortArgs a, i
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
       const uint32_t li = wbase + i * 32 + lane;
-      val[i] = (li < valid) ? __ldg(src_v + pbase + li) : 0u;
+      val[i] = (li < valid) ? ((a.vals_identity && pass == 0) ? pbase + li : __ldg(src_v + pbase + li)) : 0u;
     }
     __syncthreads();  // every wh[] has been read: its storage now takes the values
 #pragma unroll

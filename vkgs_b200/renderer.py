@@ -220,6 +220,35 @@ def reference_overlay(show_axis: bool = True, show_grid: bool = True):
     return (np.asarray(pos, np.float32).reshape(-1, 2, 3), np.asarray(col, np.float32).reshape(-1, 2, 4), model)
 
 
+def shared_create(device: int, nbytes: int):
+    """A device buffer other processes of the node can map: (device pointer, 64-byte handle)."""
+    p = C.c_void_p()
+    h = (C.c_uint8 * 64)()
+    L.check(L.lib().vkgsb_shared_create(int(device), int(nbytes), C.byref(p), h))
+    return p.value, bytes(h)
+
+
+def shared_open(device: int, handle: bytes) -> int:
+    p = C.c_void_p()
+    h = (C.c_uint8 * 64).from_buffer_copy(handle)
+    L.check(L.lib().vkgsb_shared_open(int(device), h, C.byref(p)))
+    return p.value
+
+
+def shared_close(device: int, ptr: int):
+    L.check(L.lib().vkgsb_shared_close(int(device), C.c_void_p(ptr)))
+
+
+def shared_read(device: int, ptr: int, offset: int, shape) -> np.ndarray:
+    out = np.empty(shape, np.uint8)
+    L.check(L.lib().vkgsb_shared_read(int(device), C.c_void_p(ptr), int(offset), out.size, _ptr(out)))
+    return out
+
+
+def shared_destroy(device: int, ptr: int):
+    L.check(L.lib().vkgsb_shared_destroy(int(device), C.c_void_p(ptr)))
+
+
 def device_count() -> int:
     c = C.c_int()
     L.check(L.lib().vkgsb_device_count(C.byref(c)))
