@@ -471,7 +471,7 @@ def run_views(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
     def stages(mode):
         r.set_blend_mode(mode)
         r.set_option(L.OPT_STAGE_TIMING, 1)
-        acc = dict(ms_project=0.0, ms_sort=0.0, ms_bin=0.0, ms_blend=0.0, ms_total=0.0)
+        acc = dict(ms_cull=0.0, ms_project=0.0, ms_sort=0.0, ms_bin=0.0, ms_blend=0.0, ms_total=0.0)
         vis, pairs, totals, retries = [], [], [], []
         for i in range(W + K):
             r.set_camera(block=cams[i % len(cams)])

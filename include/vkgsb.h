@@ -10,7 +10,9 @@
  *
  * Threading (same contract as the reference): one renderer = one CUDA device + one
  * stream; draw/set_* are not re-entrant per renderer; load_ply_async / load_progress / cancel_load
- * may be called from any thread.
+ * may be called from any thread.  Frames share the renderer's work buffers: a frame drawn on another stream
+ * than the previous one is ordered behind it, and loads / vkgsb_set_lines / vkgsb_destroy drain every frame
+ * issued, whichever stream it ran on.
  *
  * Matrices are column-major float[16] (m[c*4+r]) exactly as glm / the reference's UBO
  * (src/vkgs/vulkan/shader/uniforms.h:10-15).
@@ -94,6 +96,8 @@ typedef struct vkgsb_stats {
   uint32_t pad0;
   uint64_t fragment_count;      /* fragments (pixel x splat pairs inside the +-3 sigma quad) the blend stage shaded in the
                                    last frame; only counted while VKGSB_OPT_COUNT_FRAGMENTS is on */
+  float ms_cull;                /* the part of ms_project spent in the cull kernel (rank.comp equivalent) */
+  uint32_t pad1;
 } vkgsb_stats;
 
 enum vkgsb_option {
@@ -171,6 +175,10 @@ VKGSB_API int vkgsb_draw_batch(vkgsb_renderer* r, uint32_t n_views, const vkgsb_
                                size_t dst_stride, int dst_is_device, void* stream);
 VKGSB_API int vkgsb_image_device_ptr(vkgsb_renderer* r, void** ptr);
 VKGSB_API int vkgsb_sync(vkgsb_renderer* r);
+/* Frame pacing, the reference's fence wait (engine.cc:1028-1035: frame i waits for frame i - 2): blocks until the frame
+ * issued `frames_back` (1..3) frames before the NEXT one has finished on the device.  A render loop that calls this with
+ * 2 before every vkgsb_draw(dst = NULL) keeps two frames in flight instead of filling the launch queue. */
+VKGSB_API int vkgsb_wait_frame(vkgsb_renderer* r, uint32_t frames_back);
 VKGSB_API int vkgsb_get_stats(vkgsb_renderer* r, vkgsb_stats* out);
 
 /* Destinations shared between the processes of one node (one process per GPU): the consumer process
@@ -202,12 +210,18 @@ VKGSB_API int vkgsb_read_scene(vkgsb_renderer* r, float* pos, float* cov, float*
  * (vrdxCmdSortKeyValueIndirect), caller-owned storage from vkgsb_sort_storage_bytes
  * (vrdxGetSorterKeyValueStorageRequirements).  All pointers are device pointers; asynchronous on `stream`. */
 VKGSB_API int vkgsb_sort_storage_bytes(uint32_t max_element_count, size_t* bytes);
+/* d_keys must be 16-byte aligned, d_storage 256-byte (cudaMalloc alignment); fewer than 2^30 elements. */
 VKGSB_API int vkgsb_sort_key_value_indirect(void* stream, uint32_t max_element_count, const uint32_t* d_count,
                                             uint32_t* d_keys, uint32_t* d_values, void* d_storage);
 
 /* Host helper: vkgs::Camera (camera.cc:25-45) for an orbit pose; fills projection/view/camera_position, model = I. */
 VKGSB_API int vkgsb_camera_orbit(uint32_t width, uint32_t height, float fovy, float r, float phi, float theta,
                                  const float center[3], vkgsb_camera* out);
+
+/* Host helper: the viewer's mouse operations (camera.cc:47-70) applied to a default vkgs::Camera in the order Rotate(rot_x,
+ * rot_y), Zoom(zoom), SetFov(fov) if fov > 0, Translate(tx, ty, tz), DollyZoom(dolly) if dolly != 0. */
+VKGSB_API int vkgsb_camera_apply(uint32_t width, uint32_t height, float rot_x, float rot_y, float zoom, float fov,
+                                 float tx, float ty, float tz, float dolly, vkgsb_camera* out);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert C.sizeof(L.CameraBlock) == (16 + 16 + 4 + 16) * 4
     assert C.sizeof(L.Config) == 32
-    assert C.sizeof(L.Stats) == 72
+    assert C.sizeof(L.Stats) == 80
 
 
 def test_no_device_is_a_loud_error():
@@ -63,6 +63,29 @@ def test_library_camera_matches_reference_camera_cc():
         assert np.abs(np.array(cb.view[:], np.float32).reshape(4, 4) - v).max() <= 1e-7
         assert np.abs(np.array(cb.camera_position[:], np.float32) - e).max() <= 1e-7
         np.testing.assert_allclose(np.array(cb.projection[:], np.float32).reshape(4, 4), p, rtol=3e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("ops", [dict(rot_x=37.0, rot_y=-12.0), dict(zoom=25.0), dict(fov=float(np.radians(75.0))),
+                                 dict(tx=40.0, ty=-15.0, tz=8.0), dict(rot_x=-300.0, rot_y=500.0),   # phi clamps
+                                 dict(rot_x=120.0, rot_y=33.0, zoom=-40.0, fov=float(np.radians(45.0)), tx=5.0, ty=9.0, tz=-3.0)])
+def test_camera_mouse_operations_match_reference_camera_cc(ops):
+    """Camera::Rotate / Zoom / SetFov (dolly zoom) / Translate of this repo (csrc/camera.cc) against the reference's own
+    camera.cc:47-70 compiled into oracle/_ref (ref_camera_ops, oracle/ref_shim/camera_shim.cc:24-38)."""
+    import ctypes as C
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    for (w, h) in ((1600, 900), (640, 480)):
+        p, v, e = R.camera_ops(w, h, **ops)
+        cb = L.CameraBlock()
+        a = dict(rot_x=0.0, rot_y=0.0, zoom=0.0, fov=-1.0, tx=0.0, ty=0.0, tz=0.0)
+        a.update(ops)
+        L.check(L.lib().vkgsb_camera_apply(w, h, a["rot_x"], a["rot_y"], a["zoom"], a["fov"], a["tx"], a["ty"], a["tz"], 0.0,
+                                           C.byref(cb)))
+        # the same float operations in the same order; glm's trigonometry is libm's: a few ulp at most
+        np.testing.assert_allclose(np.array(cb.view[:], np.float32).reshape(4, 4), v, rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(np.array(cb.camera_position[:], np.float32), e, rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(np.array(cb.projection[:], np.float32).reshape(4, 4), p, rtol=1e-6, atol=1e-9)
 
 
 def test_golden_camera_blocks_are_reference_defaults():

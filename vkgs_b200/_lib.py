@@ -30,7 +30,8 @@ class Stats(C.Structure):
                 ("visible_point_count", C.c_uint32), ("pair_overflow", C.c_uint32), ("pair_count", C.c_uint64),
                 ("ms_project", C.c_float), ("ms_sort", C.c_float), ("ms_bin", C.c_float), ("ms_blend", C.c_float),
                 ("ms_total", C.c_float), ("frame_counter", C.c_uint64), ("blend_retries", C.c_uint32),
-                ("pad0", C.c_uint32), ("fragment_count", C.c_uint64)]
+                ("pad0", C.c_uint32), ("fragment_count", C.c_uint64), ("ms_cull", C.c_float),
+                ("pad1", C.c_uint32)]
 
 
 # every entry point include/vkgsb.h declares: name -> (restype, argtypes)
@@ -55,6 +56,7 @@ SIGNATURES = {
     "vkgsb_draw_batch": (C.c_int, [_P, C.c_uint32, C.POINTER(CameraBlock), _P, C.c_size_t, C.c_int, _P]),
     "vkgsb_image_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
     "vkgsb_sync": (C.c_int, [_P]),
+    "vkgsb_wait_frame": (C.c_int, [_P, C.c_uint32]),
     "vkgsb_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "vkgsb_row_histogram": (C.c_int, [_P, _P, C.c_uint32]),
     "vkgsb_read_sorted": (C.c_int, [_P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
@@ -69,6 +71,7 @@ SIGNATURES = {
     "vkgsb_shared_destroy": (C.c_int, [C.c_int, _P]),
     "vkgsb_camera_orbit": (C.c_int, [C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, _P,
                                      C.POINTER(CameraBlock)]),
+    "vkgsb_camera_apply": (C.c_int, [C.c_uint32, C.c_uint32] + [C.c_float] * 8 + [C.POINTER(CameraBlock)]),
 }
 
 _lib = None

@@ -83,7 +83,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
     _build_pygs(force)
+    _build_viewer(force)
     return LIB
+
+
+def _build_viewer(force: bool) -> str:
+    """vkgs_b200/lib/vkgs_viewer: the reference's examples/vkgs_viewer.cc flow compiled against this repo's
+    include/vkgs/engine/engine.h (tools/cpp/vkgs_viewer.cc) - the C++ drop-in check."""
+    src = os.path.join(ROOT, "tools", "cpp", "vkgs_viewer.cc")
+    out = os.path.join(HERE, "lib", "vkgs_viewer")
+    if not os.path.exists(src):
+        return ""
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return out
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-L", os.path.dirname(LIB), "-lvkgsb",
+           "-lpthread", "-Wl,-rpath,$ORIGIN", "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"viewer build failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 def _build_pygs(force: bool) -> str:

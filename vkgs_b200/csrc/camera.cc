@@ -134,3 +134,29 @@ extern "C" int vkgsb_camera_orbit(uint32_t width, uint32_t height, float fovy, f
   out->pad0 = 0.f;
   return VKGSB_OK;
 }
+
+// The viewer's mouse operations on a default camera, in the order Rotate, Zoom, SetFov (fov <= 0: keep), Translate,
+// DollyZoom: what Engine::Impl::Draw does with ImGui's mouse deltas (engine.cc:767-818 -> camera.cc:47-70).
+extern "C" int vkgsb_camera_apply(uint32_t width, uint32_t height, float rot_x, float rot_y, float zoom, float fov,
+                                  float tx, float ty, float tz, float dolly, vkgsb_camera* out) {
+  if (!out || width == 0 || height == 0) return VKGSB_ERR_INVALID;
+  vkgs::Camera cam;
+  cam.SetWindowSize(width, height);
+  cam.Rotate(rot_x, rot_y);
+  cam.Zoom(zoom);
+  if (fov > 0.f) cam.SetFov(fov);
+  cam.Translate(tx, ty, tz);
+  if (dolly != 0.f) cam.DollyZoom(dolly);
+  const vkgs::Mat4 p = cam.ProjectionMatrix(), v = cam.ViewMatrix();
+  const vkgs::Vec3 e = cam.Eye();
+  for (int i = 0; i < 16; ++i) {
+    out->projection[i] = p[i];
+    out->view[i] = v[i];
+    out->model[i] = (i % 5 == 0) ? 1.f : 0.f;
+  }
+  out->camera_position[0] = e[0];
+  out->camera_position[1] = e[1];
+  out->camera_position[2] = e[2];
+  out->pad0 = 0.f;
+  return VKGSB_OK;
+}

@@ -40,6 +40,10 @@ class Engine::Impl {
         pending_ply_filepath_.clear();
       }
       if (!path.empty()) LoadSplats(path);
+      // two frames in flight, like the reference's fences (engine.cc:1028-1035): frame i is issued once frame i - 2 has
+      // finished, so camera / model / viewport changes, Close() and a concurrent DrawToImage never queue behind more
+      // than two frames
+      vkgsb_wait_frame(renderer_, 2);
       if (!DrawFrame(nullptr)) std::this_thread::sleep_for(std::chrono::milliseconds(1));  // nothing resident yet
     }
     vkgsb_sync(renderer_);

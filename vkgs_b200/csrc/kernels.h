@@ -45,7 +45,8 @@ void project_configure();  // once per device: opt in to > 48 KB dynamic shared 
 // when FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control and writes
 // Control::visible_count.
 void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl, const CullIndex& ix, uint32_t* d_keys,
-                    float* d_rrec, uint32_t* d_bin_rect, float* d_inst, float* d_zndc, cudaStream_t stream);
+                    float* d_rrec, uint32_t* d_bin_rect, float* d_inst, float* d_zndc, cudaStream_t stream,
+                    cudaEvent_t after_cull = nullptr);  // recorded between the two kernels (stage timing)
 // parity taps: splat id of every visible slot of the last frame (from its cull index) -> d_vis_id
 void launch_expand_ids(const CullIndex& ix, uint32_t n, uint32_t* d_vis_id, cudaStream_t stream);
 

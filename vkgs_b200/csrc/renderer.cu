@@ -106,6 +106,8 @@ struct vkgsb_renderer {
   bool graph_valid = false;
   uint32_t graph_n = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t flight[4] = {nullptr, nullptr, nullptr, nullptr};  // end of frame f on the stream that drew it, at [f & 3]
+  cudaStream_t last_stream = nullptr;                            // the stream that drew the last frame
   bool ev_recorded = false;
   uint64_t frame_counter = 0;
   std::mutex draw_mutex;
@@ -130,6 +132,13 @@ int set_device(vkgsb_renderer* r) {
 }
 
 void invalidate_graph(vkgsb_renderer* r) { r->graph_valid = false; }
+
+// Every frame issued so far has finished - on the renderer's stream or on a caller's.
+cudaError_t drain_frames(vkgsb_renderer* r) {
+  cudaError_t e = cudaStreamSynchronize(r->stream);
+  if (e == cudaSuccess && r->frame_counter) e = cudaEventSynchronize(r->flight[r->frame_counter & 3]);
+  return e;
+}
 
 int ensure_row_staging(vkgsb_renderer* r, uint32_t stride_bytes) {
   size_t need = static_cast<size_t>(kChunkVertices) * stride_bytes;
@@ -165,7 +174,7 @@ int ingest(vkgsb_renderer* r, uint64_t n64, uint32_t stride_bytes, const uint32_
     std::lock_guard<std::mutex> g(r->draw_mutex);
     r->scene_n.store(0);
     invalidate_graph(r);
-    CU_TRY(cudaStreamSynchronize(r->stream));
+    CU_TRY(drain_frames(r));
   }
   r->total_points.store(n);
   r->loaded_points.store(0);
@@ -178,7 +187,13 @@ int ingest(vkgsb_renderer* r, uint64_t n64, uint32_t stride_bytes, const uint32_
       return fail(VKGSB_ERR_CANCELLED, "load cancelled");
     }
     const uint32_t count = static_cast<uint32_t>(std::min<uint64_t>(kChunkVertices, n - start));
-    CU_TRY(cudaEventSynchronize(r->chunk_done[buf]));  // staging buffer free again
+    CU_TRY(cudaEventSynchronize(r->chunk_done[buf]));  // staging buffer free again: chunk start - 2 chunks is resident
+    if (start >= 2ull * kChunkVertices) {
+      // like the reference, which draws the loaded_point_count splats parsed so far (engine.cc:1137-1160): everything
+      // before the chunk still in flight is published to the frame path
+      std::lock_guard<std::mutex> g(r->draw_mutex);
+      r->scene_n.store(static_cast<uint32_t>(start - kChunkVertices));
+    }
     if (!fill(r->h_rows[buf], start, count)) {
       cudaStreamSynchronize(r->load_stream);
       return fail(VKGSB_ERR_IO, "short read at vertex " + std::to_string(start));
@@ -305,23 +320,19 @@ void fill_params(vkgsb_renderer* r) {
     const bool shaped = P[1] == 0.f && P[2] == 0.f && P[3] == 0.f && P[4] == 0.f && P[6] == 0.f && P[7] == 0.f &&
                         P[8] == 0.f && P[9] == 0.f && P[11] == -1.f && P[12] == 0.f && P[13] == 0.f && P[15] == 0.f;
     const bool banded = p.band_y0 > 0u || p.band_y1 < p.height;
-    // |W|_2^2 = largest eigenvalue of W^T W (power iteration in double; never above the Frobenius bound), + 1 %
-    double G[9], v[3] = {1.0, 1.0, 1.0}, wf2 = 0.0, lam = 0.0;
+    // |W|_2^2 = largest eigenvalue of G = W^T W, bounded from above two ways: Gershgorin (the largest absolute row sum
+    // of G - exact for a uniformly scaled rotation, the usual model matrix) and the trace (the Frobenius norm of W).
+    // Both are upper bounds for every W, so their minimum is one.
+    double G[9], wf2 = 0.0, gersh = 0.0;
     for (int a = 0; a < 3; ++a)
       for (int b = 0; b < 3; ++b) {
         G[a * 3 + b] = 0.0;
         for (int k = 0; k < 3; ++k) G[a * 3 + b] += static_cast<double>(p.w3[a * 3 + k]) * p.w3[b * 3 + k];
       }
     for (int i = 0; i < 9; ++i) wf2 += static_cast<double>(p.w3[i]) * p.w3[i];
-    for (int it = 0; it < 64; ++it) {
-      double u[3];
-      for (int a = 0; a < 3; ++a) u[a] = G[a * 3 + 0] * v[0] + G[a * 3 + 1] * v[1] + G[a * 3 + 2] * v[2];
-      lam = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-      if (!(lam > 0.0)) break;
-      for (int a = 0; a < 3; ++a) v[a] = u[a] / lam;
-    }
-    double w2 = std::min(wf2, lam * 1.01);
-    if (!(w2 > 0.0) || !(lam > 0.0)) w2 = wf2;  // degenerate or non-finite model: the Frobenius bound, or NaN (keeps everything)
+    for (int a = 0; a < 3; ++a) gersh = std::max(gersh, std::fabs(G[a * 3]) + std::fabs(G[a * 3 + 1]) + std::fabs(G[a * 3 + 2]));
+    double w2 = std::min(wf2, gersh) * (1.0 + 1e-6);
+    if (!(w2 > 0.0)) w2 = wf2;  // degenerate or non-finite model: NaN keeps everything
     const float hh = 0.5f * fh;
     p.bc_a = static_cast<float>(9.0 * hh * hh * w2);
     p.bc_b = 9.f * hh * hh * (p.lpx + p.lpy);
@@ -342,7 +353,7 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   if (timed) CU_TRY(cudaEventRecord(r->ev[0], s));
   // the depth sort runs an odd number of passes: its input goes to the ping-pong side, its result lands in keys / slots
   launch_project(sc, r->d_fp, r->ctrl, r->cull, r->keys_alt, r->rrec, r->bin_rect, r->inst,
-                 r->n_lines ? r->zndc : nullptr, s);
+                 r->n_lines ? r->zndc : nullptr, s, timed ? r->ev[5] : nullptr);
   if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
   SortArgs depth{};
   depth.d_count = &r->ctrl->visible_count;
@@ -375,7 +386,11 @@ int run_frame(vkgsb_renderer* r, cudaStream_t s, void* direct_dst = nullptr) {
   if (!r->have_cam) return fail(VKGSB_ERR_INVALID, "vkgsb_set_camera has not been called");
   if (r->width == 0 || r->height == 0) return fail(VKGSB_ERR_INVALID, "vkgsb_set_viewport has not been called");
   const uint32_t n = r->scene_n.load();
-  if (n == 0) return fail(VKGSB_ERR_NO_SCENE, "no splats loaded");
+  // nothing resident: an error, unless a load is under way or lines are set - the reference's window shows the clear
+  // colour and the axis / grid while the first chunks are parsed
+  if (n == 0 && r->n_lines == 0 && r->load_state.load() != 1) return fail(VKGSB_ERR_NO_SCENE, "no splats loaded");
+  // the work buffers are shared by all frames: a frame on another stream than the last one waits for it
+  if (r->frame_counter && s != r->last_stream) CU_TRY(cudaStreamWaitEvent(s, r->flight[r->frame_counter & 3], 0));
   fill_params(r);
   r->h_fp.pad4 = 0u;
   r->h_fp.dst_image = reinterpret_cast<unsigned long long>(direct_dst);
@@ -405,6 +420,8 @@ int run_frame(vkgsb_renderer* r, cudaStream_t s, void* direct_dst = nullptr) {
     r->ev_recorded = false;
   }
   r->frame_counter++;
+  r->last_stream = s;
+  CU_TRY(cudaEventRecord(r->flight[r->frame_counter & 3], s));
   r->last_frame_has_instances = r->keep_instances != 0;
   return VKGSB_OK;
 }
@@ -507,6 +524,8 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   for (auto& ev : r->chunk_done)
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  for (auto& ev : r->flight)
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   blend_configure();
   project_configure();
   r->loader = std::thread(loader_main, r);
@@ -526,7 +545,7 @@ void vkgsb_destroy(vkgsb_renderer* r) {
     r->loader.join();
   }
   cudaSetDevice(r->device);
-  if (r->stream) cudaStreamSynchronize(r->stream);
+  if (r->stream) drain_frames(r);
   if (r->load_stream) cudaStreamSynchronize(r->load_stream);
   if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
   void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
@@ -541,6 +560,8 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   for (auto& ev : r->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : r->chunk_done)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : r->flight)
     if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) {
     if (r->frame_done[i]) cudaEventDestroy(r->frame_done[i]);
@@ -669,7 +690,7 @@ int vkgsb_set_lines(vkgsb_renderer* r, uint32_t n_lines, const float* positions,
   if (n_lines > (1u << 20)) return fail(VKGSB_ERR_CAPACITY, "at most 2^20 lines");
   if (set_device(r)) return VKGSB_ERR_CUDA;
   std::lock_guard<std::mutex> g(r->draw_mutex);
-  CU_TRY(cudaStreamSynchronize(r->stream));  // frames in flight still read the old geometry
+  CU_TRY(drain_frames(r));  // frames in flight still read the old geometry
   invalidate_graph(r);
   if (r->line_pos) cudaFree(r->line_pos);
   if (r->line_col) cudaFree(r->line_col);
@@ -751,7 +772,20 @@ int vkgsb_image_device_ptr(vkgsb_renderer* r, void** ptr) {
 int vkgsb_sync(vkgsb_renderer* r) {
   if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
   if (set_device(r)) return VKGSB_ERR_CUDA;
-  CU_TRY(cudaStreamSynchronize(r->stream));
+  CU_TRY(drain_frames(r));
+  return VKGSB_OK;
+}
+
+int vkgsb_wait_frame(vkgsb_renderer* r, uint32_t frames_back) {
+  if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
+  if (frames_back == 0 || frames_back > 3) return fail(VKGSB_ERR_INVALID, "frames_back must be 1, 2 or 3");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  uint64_t f;
+  {
+    std::lock_guard<std::mutex> g(r->draw_mutex);
+    f = r->frame_counter + 1;  // the frame the caller is about to issue
+  }
+  if (f > frames_back) CU_TRY(cudaEventSynchronize(r->flight[(f - frames_back) & 3]));
   return VKGSB_OK;
 }
 
@@ -771,6 +805,7 @@ int vkgsb_get_stats(vkgsb_renderer* r, vkgsb_stats* out) {
   out->frame_counter = r->frame_counter;
   if (r->ev_recorded) {
     CU_TRY(cudaEventElapsedTime(&out->ms_project, r->ev[0], r->ev[1]));
+    CU_TRY(cudaEventElapsedTime(&out->ms_cull, r->ev[0], r->ev[5]));
     CU_TRY(cudaEventElapsedTime(&out->ms_sort, r->ev[1], r->ev[2]));
     CU_TRY(cudaEventElapsedTime(&out->ms_bin, r->ev[2], r->ev[3]));
     CU_TRY(cudaEventElapsedTime(&out->ms_blend, r->ev[3], r->ev[4]));
@@ -949,7 +984,10 @@ int vkgsb_sort_key_value_indirect(void* stream, uint32_t max_element_count, cons
                                   uint32_t* d_values, void* d_storage) {
   if (max_element_count == 0) return VKGSB_OK;  // nothing to sort; pointers are not inspected
   if (!d_count || !d_keys || !d_values || !d_storage) return fail(VKGSB_ERR_INVALID, "null device pointer");
-  if (max_element_count > (1u << 30)) return fail(VKGSB_ERR_CAPACITY, "at most 2^30 elements");
+  if (max_element_count >= (1u << 30)) return fail(VKGSB_ERR_CAPACITY, "fewer than 2^30 elements");
+  if ((reinterpret_cast<uintptr_t>(d_keys) & 15u) || (reinterpret_cast<uintptr_t>(d_values) & 3u) ||
+      (reinterpret_cast<uintptr_t>(d_storage) & 255u))
+    return fail(VKGSB_ERR_INVALID, "d_keys must be 16-byte aligned (it is read as uint4), d_values 4-byte, d_storage 256-byte");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   size_t off_lb, off_k, off_v;
   sort_storage_layout(max_element_count, &off_lb, &off_k, &off_v);
