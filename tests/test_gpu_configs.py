@@ -125,3 +125,34 @@ def test_c5_shaped_large_scene_in_bands():
         assert r.stats()["visible_point_count"] == st["visible_point_count"]   # ... which keeps the whole visible set
         r.set_option(vkgs_b200.OPT_BAND_CULL, 1)
         r.set_band(0, 0)
+
+
+def test_band_cull_is_conservative_under_a_nonuniformly_scaled_model():
+    """The band cull's footprint bound uses an upper bound of |mat3(view) mat3(model)|_2 (fill_params, renderer.cu): with
+    a non-uniformly scaled, rotated model matrix the bands must still concatenate to the full frame bit for bit."""
+    w, h = 800, 600
+    rows = synth.scene_c1(n=60_000, seed=21)
+    a, b = np.radians(33.0), np.radians(-58.0)
+    ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+    for scale in ((3.0, 0.4, 1.0), (0.3, 0.3, 2.5), (1.0, 4.0, 0.5)):
+        m = np.eye(4, dtype=np.float32)
+        m[:3, :3] = (ry @ rx @ np.diag(scale)).astype(np.float32)
+        model = m.T.copy()                                                  # column-major
+        with vkgs_b200.Renderer(max_splats=rows.shape[0], max_width=w, max_height=h, max_pairs=1 << 25) as r:
+            r.upload_splats(rows)
+            cam = pycam.orbit(w, h, r=4.0, phi_deg=65.0, theta_deg=20.0)
+            r.set_viewport(w, h)
+            r.set_camera(cam.projection_matrix(), cam.view_matrix(), cam.eye(), model)
+            img = r.draw().copy()
+            full_visible = r.stats()["visible_point_count"]
+            assert r.stats()["pair_overflow"] == 0 and img[..., :3].max() > 0
+            out = np.zeros_like(img)
+            culled = 0
+            for y0, y1 in ((0, 100), (100, 290), (290, 310), (310, h)):
+                r.set_band(y0, y1)
+                out[y0:y1] = r.draw()[y0:y1]
+                culled += full_visible - r.stats()["visible_point_count"]
+            r.set_band(0, 0)
+            assert np.array_equal(out, img), f"scale {scale}"
+            assert culled > 0                                               # the cull did drop splats somewhere

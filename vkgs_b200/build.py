@@ -31,9 +31,9 @@ SOURCES = {
     "project.cu": ["-fmad=false"] + os.environ.get("VKGSB_PROJECT_FLAGS", "").split(),
     "load.cu": ["-fmad=false"],
     "lines.cu": ["-fmad=false"],
-    "sort.cu": [],
-    "bin.cu": [],
-    "blend.cu": [],
+    "sort.cu": os.environ.get("VKGSB_SORT_FLAGS", "").split(),
+    "bin.cu": os.environ.get("VKGSB_BIN_FLAGS", "").split(),
+    "blend.cu": os.environ.get("VKGSB_BLEND_FLAGS", "").split(),
     "renderer.cu": [],
     "ply.cc": [],
     "camera.cc": [],

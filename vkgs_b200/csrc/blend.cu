@@ -87,7 +87,7 @@ __device__ __forceinline__ uint32_t subtile_mask(uint32_t x0, uint32_t x1, uint3
 // COUNT: also count the fragments shaded (pixel x splat pairs inside the +-3 sigma square that reach the blend
 // arithmetic) into Control::fragment_count - the work unit of this stage; off on the timed path.
 template <int MODE, bool LAYER, int ROWS, bool COUNT>
-__global__ void __launch_bounds__(128 * ROWS, MODE == VKGSB_BLEND_FP32_MODE ? 1024 / (128 * ROWS) : 1)
+__global__ void __launch_bounds__(128 * ROWS, MODE == VKGSB_BLEND_FP32_MODE ? 1024 / (128 * ROWS) : 512 / (128 * ROWS))
 k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const uint2* __restrict__ ranges,
         const uint32_t* __restrict__ pair_rank, const float4* __restrict__ rrec, int bgra, uint32_t reg_y0,
         const unsigned long long* __restrict__ layer, const float* __restrict__ zndc, uint8_t* __restrict__ image) {

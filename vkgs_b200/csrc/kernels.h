@@ -41,12 +41,14 @@ struct CullIndexLayout {
 };
 CullIndexLayout cull_index_layout(uint32_t max_splats);
 void project_configure();  // once per device: opt in to > 48 KB dynamic shared memory
-// k_cull + k_project.  d_rrec: 3 x float4 raster record per visible slot; d_inst: 12-float instance record (written only
-// when FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control and writes
+// k_cull: the scene's centres -> cull index `ix` (its upper levels zero on entry).  Reads only the parameter block and
+// the scene, so a frame's cull may run while the previous frame is still in its later stages.
+void launch_cull(const Scene& scene, const FrameParams* d_fp, const CullIndex& ix, cudaStream_t stream);
+// k_project.  d_rrec: 3 x float4 raster record per visible slot; d_inst: 12-float instance record (written only when
+// FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control and writes
 // Control::visible_count.
 void launch_project(const Scene& scene, const FrameParams* d_fp, Control* d_ctrl, const CullIndex& ix, uint32_t* d_keys,
-                    float* d_rrec, uint32_t* d_bin_rect, float* d_inst, float* d_zndc, cudaStream_t stream,
-                    cudaEvent_t after_cull = nullptr);  // recorded between the two kernels (stage timing)
+                    float* d_rrec, uint32_t* d_bin_rect, float* d_inst, float* d_zndc, cudaStream_t stream);
 // parity taps: splat id of every visible slot of the last frame (from its cull index) -> d_vis_id
 void launch_expand_ids(const CullIndex& ix, uint32_t n, uint32_t* d_vis_id, cudaStream_t stream);
 

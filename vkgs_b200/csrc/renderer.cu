@@ -70,12 +70,19 @@ struct vkgsb_renderer {
   uint32_t* bin_slots = nullptr;   // splat slots by coarse bin, nearest first (bin.cu); capacity max_pairs
   BinScratch bin{};
   uint32_t* lookback_depth = nullptr;
-  uint8_t* zero_region = nullptr;  // Control | upper levels of the cull index's count tree | coarse-bin ranges
+  uint8_t* zero_region = nullptr;  // Control | coarse-bin ranges
   size_t zero_bytes = 0;
   Control* ctrl = nullptr;
-  CullIndex cull{};                // k_cull -> k_project (project.cu)
+  // Two copies, used by alternate frames, of what a frame's cull needs and leaves: the parameter block and the cull index
+  // (k_cull -> k_project, project.cu).  Frame f + 1's cull then runs on cull_stream while frame f is still in its
+  // projection / sort / binning / blend on the frame's stream.
+  CullIndex cull[2]{};
+  uint32_t* cull_tree[2] = {nullptr, nullptr};  // the upper levels of cull[p]'s count tree: zeroed before every cull
+  size_t cull_tree_bytes = 0;
+  cudaStream_t cull_stream = nullptr;
+  cudaEvent_t cull_done[2] = {nullptr, nullptr};
   uint2* ranges = nullptr;
-  FrameParams* d_fp = nullptr;
+  FrameParams* d_fp[2] = {nullptr, nullptr};
   uint8_t* image = nullptr;
   // draw_batch to host memory: frame i is copied out of stage[i & 1] on copy_stream while frame i + 1 renders
   uint8_t* stage[2] = {nullptr, nullptr};
@@ -102,9 +109,11 @@ struct vkgsb_renderer {
   uint32_t band_y0 = 0, band_y1 = 0;
   int band_cull = 1;  // VKGSB_OPT_BAND_CULL
   FrameParams h_fp{};
-  cudaGraphExec_t graph_exec = nullptr;
-  bool graph_valid = false;
-  uint32_t graph_n = 0;
+  // per parity: the cull graph (cull_stream) and the rest of the frame (the frame's stream); valid for one
+  // (n, viewport, band, mode, format)
+  cudaGraphExec_t graph_cull[2] = {nullptr, nullptr}, graph_main[2] = {nullptr, nullptr};
+  bool graph_valid[2] = {false, false};
+  uint32_t graph_n[2] = {0, 0};
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t flight[4] = {nullptr, nullptr, nullptr, nullptr};  // end of frame f on the stream that drew it, at [f & 3]
   cudaStream_t last_stream = nullptr;                            // the stream that drew the last frame
@@ -131,11 +140,12 @@ int set_device(vkgsb_renderer* r) {
   return VKGSB_OK;
 }
 
-void invalidate_graph(vkgsb_renderer* r) { r->graph_valid = false; }
+void invalidate_graph(vkgsb_renderer* r) { r->graph_valid[0] = r->graph_valid[1] = false; }
 
 // Every frame issued so far has finished - on the renderer's stream or on a caller's.
 cudaError_t drain_frames(vkgsb_renderer* r) {
   cudaError_t e = cudaStreamSynchronize(r->stream);
+  if (e == cudaSuccess && r->cull_stream) e = cudaStreamSynchronize(r->cull_stream);
   if (e == cudaSuccess && r->frame_counter) e = cudaEventSynchronize(r->flight[r->frame_counter & 3]);
   return e;
 }
@@ -342,18 +352,34 @@ void fill_params(vkgsb_renderer* r) {
   }
 }
 
-// Stage kernels of one frame on `s`.  With `timed`, CUDA events bracket the stages (ev[0..4]).
-int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
+// The cull of a frame (parity p) on `s`: count tree cleared, k_cull.
+int record_cull(vkgsb_renderer* r, int p, cudaStream_t s, bool clear = true) {
   const uint32_t n = r->scene_n.load();
   Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, n};
+  if (clear) CU_TRY(cudaMemsetAsync(r->cull_tree[p], 0, r->cull_tree_bytes, s));
+  launch_cull(sc, r->d_fp[p], r->cull[p], s);
+  CU_TRY(cudaGetLastError());
+  return VKGSB_OK;
+}
+
+// What a frame clears and draws before its splat stages, on `s`.
+int record_clears(vkgsb_renderer* r, int p, cudaStream_t s) {
+  const uint32_t n = r->scene_n.load();
   CU_TRY(cudaMemsetAsync(r->zero_region, 0, r->zero_bytes, s));
   // look-back words of the depth sort: only partitions of the <= n visible splats can be touched
   CU_TRY(cudaMemsetAsync(r->lookback_depth, 0, sort_lookback_bytes(n), s));
-  if (r->n_lines) launch_lines(r->d_fp, r->n_lines, r->line_pos, r->line_col, r->width, r->height, r->layer, s);
-  if (timed) CU_TRY(cudaEventRecord(r->ev[0], s));
+  if (r->n_lines) launch_lines(r->d_fp[p], r->n_lines, r->line_pos, r->line_col, r->width, r->height, r->layer, s);
+  return VKGSB_OK;
+}
+
+// The stages behind the cull on `s`.  With `timed`, CUDA events bracket the stages (the caller records ev[0] before the
+// cull and ev[5] behind it).
+int record_stages(vkgsb_renderer* r, int p, cudaStream_t s, bool timed) {
+  const uint32_t n = r->scene_n.load();
+  Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, n};
+  FrameParams* d_fp = r->d_fp[p];
   // the depth sort runs an odd number of passes: its input goes to the ping-pong side, its result lands in keys / slots
-  launch_project(sc, r->d_fp, r->ctrl, r->cull, r->keys_alt, r->rrec, r->bin_rect, r->inst,
-                 r->n_lines ? r->zndc : nullptr, s, timed ? r->ev[5] : nullptr);
+  launch_project(sc, d_fp, r->ctrl, r->cull[p], r->keys_alt, r->rrec, r->bin_rect, r->inst, r->n_lines ? r->zndc : nullptr, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
   SortArgs depth{};
   depth.d_count = &r->ctrl->visible_count;
@@ -370,9 +396,9 @@ int record_stages(vkgsb_renderer* r, cudaStream_t s, bool timed) {
   depth.vals_identity = true;  // the value is the compacted slot: generated by the first pass
   launch_sort(depth, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[2], s));
-  launch_bin(r->d_fp, r->h_fp.ncbins, r->ctrl, r->slots, r->bin_rect, n, r->max_pairs, r->bin, r->ranges, r->bin_slots, s);
+  launch_bin(d_fp, r->h_fp.ncbins, r->ctrl, r->slots, r->bin_rect, n, r->max_pairs, r->bin, r->ranges, r->bin_slots, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[3], s));
-  launch_blend(r->d_fp, r->h_fp, r->ctrl, r->ranges, r->bin_slots, r->rrec, r->blend_mode,
+  launch_blend(d_fp, r->h_fp, r->ctrl, r->ranges, r->bin_slots, r->rrec, r->blend_mode,
                r->pixel_format == VKGSB_FORMAT_BGRA8, r->count_fragments != 0, r->n_lines ? r->layer : nullptr, r->n_lines ? r->zndc : nullptr,
                r->image, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[4], s));
@@ -394,29 +420,53 @@ int run_frame(vkgsb_renderer* r, cudaStream_t s, void* direct_dst = nullptr) {
   fill_params(r);
   r->h_fp.pad4 = 0u;
   r->h_fp.dst_image = reinterpret_cast<unsigned long long>(direct_dst);
-  k_set_params<<<1, 32, 0, s>>>(r->h_fp, r->d_fp);
+  const uint64_t f = r->frame_counter + 1;  // this frame
+  const int p = static_cast<int>(f & 1);
   if (r->stage_timing) {
-    if (int e = record_stages(r, s, true)) return e;
+    // eager, everything on the frame's stream, events between the stages
+    k_set_params<<<1, 32, 0, s>>>(r->h_fp, r->d_fp[p]);
+    CU_TRY(cudaMemsetAsync(r->cull_tree[p], 0, r->cull_tree_bytes, s));
+    if (int e = record_clears(r, p, s)) return e;
+    CU_TRY(cudaEventRecord(r->ev[0], s));
+    if (int e = record_cull(r, p, s, false)) return e;
+    CU_TRY(cudaEventRecord(r->ev[5], s));
+    if (int e = record_stages(r, p, s, true)) return e;
     r->ev_recorded = true;
   } else {
-    // the graph is captured on the renderer's own stream and is valid for one (n, viewport, band, mode, format)
-    if (!r->graph_valid || r->graph_n != n) {
-      if (r->graph_exec) {
-        cudaGraphExecDestroy(r->graph_exec);
-        r->graph_exec = nullptr;
-      }
+    if (!r->graph_valid[p] || r->graph_n[p] != n) {
+      for (cudaGraphExec_t* g : {&r->graph_cull[p], &r->graph_main[p]})
+        if (*g) {
+          cudaGraphExecDestroy(*g);
+          *g = nullptr;
+        }
       cudaGraph_t graph = nullptr;
-      CU_TRY(cudaStreamBeginCapture(r->stream, cudaStreamCaptureModeThreadLocal));
-      int e = record_stages(r, r->stream, false);
-      cudaError_t ce = cudaStreamEndCapture(r->stream, &graph);
+      CU_TRY(cudaStreamBeginCapture(r->cull_stream, cudaStreamCaptureModeThreadLocal));
+      int e = record_cull(r, p, r->cull_stream);
+      cudaError_t ce = cudaStreamEndCapture(r->cull_stream, &graph);
       if (e) return e;
       CU_TRY(ce);
-      CU_TRY(cudaGraphInstantiate(&r->graph_exec, graph, 0));
+      CU_TRY(cudaGraphInstantiate(&r->graph_cull[p], graph, 0));
       cudaGraphDestroy(graph);
-      r->graph_valid = true;
-      r->graph_n = n;
+      CU_TRY(cudaStreamBeginCapture(r->stream, cudaStreamCaptureModeThreadLocal));
+      e = record_clears(r, p, r->stream);
+      if (!e) e = record_stages(r, p, r->stream, false);
+      ce = cudaStreamEndCapture(r->stream, &graph);
+      if (e) return e;
+      CU_TRY(ce);
+      CU_TRY(cudaGraphInstantiate(&r->graph_main[p], graph, 0));
+      cudaGraphDestroy(graph);
+      r->graph_valid[p] = true;
+      r->graph_n[p] = n;
     }
-    CU_TRY(cudaGraphLaunch(r->graph_exec, s));
+    // The cull reads the scene and its parity's parameter block only: it runs on cull_stream as soon as frame f - 2
+    // (the last reader of that parameter block and cull index) has finished - that is, beside frame f - 1's later stages
+    // when frames are issued back to back.  The rest of the frame follows on the frame's stream.
+    if (f > 2) CU_TRY(cudaStreamWaitEvent(r->cull_stream, r->flight[(f - 2) & 3], 0));
+    k_set_params<<<1, 32, 0, r->cull_stream>>>(r->h_fp, r->d_fp[p]);
+    CU_TRY(cudaGraphLaunch(r->graph_cull[p], r->cull_stream));
+    CU_TRY(cudaEventRecord(r->cull_done[p], r->cull_stream));
+    CU_TRY(cudaStreamWaitEvent(s, r->cull_done[p], 0));
+    CU_TRY(cudaGraphLaunch(r->graph_main[p], s));
     r->ev_recorded = false;
   }
   r->frame_counter++;
@@ -481,6 +531,9 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   if ((e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&r->load_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&r->cull_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  for (auto& ev : r->cull_done)
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
   for (int i = 0; i < 2; ++i) {
     if ((e = cudaEventCreateWithFlags(&r->frame_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     if ((e = cudaEventCreateWithFlags(&r->copy_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
@@ -502,17 +555,20 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats));
   const CullIndexLayout cl = cull_index_layout(r->max_splats);
   const size_t ctrl_bytes = (sizeof(Control) + 255) & ~size_t(255);
-  const size_t tree_words = (static_cast<size_t>(cl.na) + cl.nb + cl.nc + 63) & ~size_t(63);
-  r->zero_bytes = ctrl_bytes + tree_words * 4 + kMaxCoarseBins * sizeof(uint2);
+  r->zero_bytes = ctrl_bytes + kMaxCoarseBins * sizeof(uint2);
   ALLOC(r->zero_region, r->zero_bytes);
   r->ctrl = reinterpret_cast<Control*>(r->zero_region);
-  r->cull.lvl_a = reinterpret_cast<uint32_t*>(r->zero_region + ctrl_bytes);
-  r->cull.lvl_b = r->cull.lvl_a + cl.na;
-  r->cull.lvl_c = r->cull.lvl_b + cl.nb;
-  r->ranges = reinterpret_cast<uint2*>(r->cull.lvl_a + tree_words);
-  ALLOC(r->cull.mask, static_cast<size_t>(cl.tiles) * 8 * 4);
-  ALLOC(r->cull.tile_cnt, static_cast<size_t>(cl.tiles) * 4);
-  ALLOC(r->d_fp, sizeof(FrameParams));
+  r->ranges = reinterpret_cast<uint2*>(r->zero_region + ctrl_bytes);
+  r->cull_tree_bytes = ((static_cast<size_t>(cl.na) + cl.nb + cl.nc + 63) & ~size_t(63)) * 4;
+  for (int p = 0; p < 2; ++p) {
+    ALLOC(r->cull_tree[p], r->cull_tree_bytes);
+    r->cull[p].lvl_a = r->cull_tree[p];
+    r->cull[p].lvl_b = r->cull[p].lvl_a + cl.na;
+    r->cull[p].lvl_c = r->cull[p].lvl_b + cl.nb;
+    ALLOC(r->cull[p].mask, static_cast<size_t>(cl.tiles) * 8 * 4);
+    ALLOC(r->cull[p].tile_cnt, static_cast<size_t>(cl.tiles) * 4);
+    ALLOC(r->d_fp[p], sizeof(FrameParams));
+  }
   ALLOC(r->image, static_cast<size_t>(r->max_width) * r->max_height * 4);
   ALLOC(r->stage[0], static_cast<size_t>(r->max_width) * r->max_height * 4);
   ALLOC(r->stage[1], static_cast<size_t>(r->max_width) * r->max_height * 4);
@@ -547,10 +603,12 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   cudaSetDevice(r->device);
   if (r->stream) drain_frames(r);
   if (r->load_stream) cudaStreamSynchronize(r->load_stream);
-  if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
+  for (cudaGraphExec_t g : {r->graph_cull[0], r->graph_cull[1], r->graph_main[0], r->graph_main[1]})
+    if (g) cudaGraphExecDestroy(g);
   void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
                  r->vis_id, r->inst, r->rrec, r->bin_rect, r->bin_slots, r->bin.tile_pairs, r->bin.tile_item, r->bin.tile_bin, r->bin.bin_total,
-                 r->lookback_depth, r->zero_region, r->cull.mask, r->cull.tile_cnt, r->d_fp, r->image, r->stage[0], r->stage[1], r->d_offsets, r->d_rows[0],
+                 r->lookback_depth, r->zero_region, r->cull[0].mask, r->cull[0].tile_cnt, r->cull[1].mask, r->cull[1].tile_cnt,
+                 r->cull_tree[0], r->cull_tree[1], r->d_fp[0], r->d_fp[1], r->image, r->stage[0], r->stage[1], r->d_offsets, r->d_rows[0],
                  r->d_rows[1], r->line_pos, r->line_col, r->zndc, r->layer};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -570,6 +628,9 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   if (r->stream) cudaStreamDestroy(r->stream);
   if (r->load_stream) cudaStreamDestroy(r->load_stream);
   if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+  if (r->cull_stream) cudaStreamDestroy(r->cull_stream);
+  for (auto& ev : r->cull_done)
+    if (ev) cudaEventDestroy(ev);
   delete r;
 }
 
@@ -835,7 +896,7 @@ int vkgsb_read_sorted(vkgsb_renderer* r, uint32_t* keys, uint32_t* ids, uint32_t
   }
   if (ids) {
     // slots_alt is free between frames: gather ids there; the ids by slot come from the frame's cull index
-    launch_expand_ids(r->cull, r->scene_n.load(), r->vis_id, r->stream);
+    launch_expand_ids(r->cull[r->frame_counter & 1], r->scene_n.load(), r->vis_id, r->stream);
     launch_gather_sorted(r->ctrl, r->slots, r->vis_id, r->inst, v, r->slots_alt, nullptr, r->stream);
     CU_TRY(cudaStreamSynchronize(r->stream));
     CU_TRY(cudaMemcpy(ids, r->slots_alt, v * 4ull, cudaMemcpyDeviceToHost));

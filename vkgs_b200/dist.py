@@ -49,20 +49,15 @@ def balanced_band_edges(row_load, world: int, min_rows: int = 8) -> List[int]:
 
 
 def gather_images(local, dst: int = 0, group=None):
-    """Gather equally shaped uint8 image tensors [B,H,W,4] to rank `dst`.  Returns the list on dst, else None."""
+    """Gather equally shaped uint8 image tensors [B,H,W,4] to rank `dst` (NCCL on GPUs, gloo in the CPU tests).
+    Returns the list on dst, else None.  On one node bench.py prefers rendering straight into rank dst's memory
+    (vkgsb_shared_*, no collective); this is the portable path."""
+    import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     if world == 1:
         return [local]
-    rank = dist.get_rank(group)
-    if dist.get_backend(group) == "nccl":
-        # NCCL has no native gather in older torch builds for uint8 lists; all ranks send, dst receives
-        import torch
-        outs = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
-        dist.gather(local, outs, dst=dst, group=group)
-        return outs
-    import torch
-    outs = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
+    outs = [torch.empty_like(local) for _ in range(world)] if dist.get_rank(group) == dst else None
     dist.gather(local, outs, dst=dst, group=group)
     return outs
 
