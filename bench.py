@@ -171,8 +171,8 @@ def ncu_traffic():
 def cpu_sample(cfg, rows, view=0, state=None):
     """One step of the CPU arm: the CPU restatement of the reference path (oracle/, C + OpenMP on all host cores) on a
     bounded sample of one frame of the workload - the whole cull, sort and projection of the view, and the rasteriser
-    (the reference's UNORM8 blend, mode 1) on 8 bands of 16 rows spread evenly over the image height, scaled to the
-    full height.  Returns (frames/s estimate, seconds this step really took, description)."""
+    (every fragment through the reference's UNORM8 blend, mode 1) on one 16-row band per host thread (4..16 bands) spread
+    evenly over the image height, scaled to the full height.  Returns (frames/s estimate, seconds this step really took, description)."""
     from oracle import oracle as O
     from vkgs_b200 import synth
     O.use_all_cores()
@@ -191,16 +191,15 @@ def cpu_sample(cfg, rows, view=0, state=None):
     t2 = time.perf_counter()
     inst = O.project(scene, ids, cam, 0)
     t3 = time.perf_counter()
-    nb, band_rows = 8, 16
+    nb, band_rows = max(4, min(O.num_threads(), 16)), 16          # one tile band per host thread
     starts = [((h - band_rows) * (2 * b + 1) // (2 * nb)) // 16 * 16 for b in range(nb)]
-    for y0 in starts:
-        O.raster_rows(inst, w, h, y0, y0 + band_rows, mode=1)
+    O.raster_band_list(inst, w, h, [y0 // 16 for y0 in starts], mode=1)     # one thread per band
     t4 = time.perf_counter()
     sampled = nb * band_rows
     frame_s = (t3 - t0) + (t4 - t3) * h / sampled
     desc = (f"1 frame of view {view}, V={len(ids)}: full cull {1e3*(t1-t0):.0f} ms + sort {1e3*(t2-t1):.0f} ms + projection "
-            f"{1e3*(t3-t2):.0f} ms; rasteriser (UNORM8 blend) on {nb} bands of {band_rows} rows at y={starts} "
-            f"{1e3*(t4-t3):.0f} ms scaled x{h/sampled:.2f}")
+            f"{1e3*(t3-t2):.0f} ms; rasteriser (every fragment, UNORM8 blend: the reference's ROP has no early exit) on {nb} "
+            f"bands of {band_rows} rows at y={starts}, one thread per band, {1e3*(t4-t3):.0f} ms scaled x{h/sampled:.2f}")
     return 1.0 / frame_s, t4 - t0, desc, O.num_threads()
 
 
@@ -277,13 +276,14 @@ class PeerWrite:
     (never reached inside a timed region shorter than `slots` steps)."""
     name = "every rank's blend kernel writes its pixels into rank 0's buffer over NVLink (CUDA IPC peer mapping, no NCCL on the data path)"
 
-    def __init__(self, torch, dist, dev, world, rank, h, w, local, slots):
+    def __init__(self, torch, dist, dev, world, rank, h, w, local, slots, images_per_slot=None):
         import vkgs_b200
         self.dist, self.world, self.rank, self.slots = dist, world, rank, slots
         self.img = h * w * 4
         self.V = vkgs_b200
+        per_slot = world if images_per_slot is None else images_per_slot
         if rank == 0:
-            self.base, handle = vkgs_b200.shared_create(local, slots * world * self.img)
+            self.base, handle = vkgs_b200.shared_create(local, slots * per_slot * self.img)
         else:
             self.base, handle = 0, b""
         obj = [handle]
@@ -589,8 +589,7 @@ def run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
         edges = [0, H_]
     img_bytes = W_ * H_ * 4
     if world > 1 and args.gather == "peer":
-        deliver = PeerWrite(torch, dist, dev, 1, 0 if rank == 0 else 1, H_, W_, local, 2)   # ONE frame per slot: every rank writes its rows of it
-        deliver.rank, deliver.world = 0, 1
+        deliver = PeerWrite(torch, dist, dev, world, rank, H_, W_, local, 2, images_per_slot=1)  # ONE frame per slot: every rank writes its rows of it
     else:
         deliver = None
         frame = torch.zeros((H_, W_, 4), dtype=torch.uint8, device=dev)
@@ -642,7 +641,6 @@ def run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
     slowest = vdist.max_over_ranks(acc["total"], dev)
     if deliver is not None:
         barrier()
-        deliver.rank = 0 if rank == 0 else 1
         deliver.close()
     if rank != 0:
         return None

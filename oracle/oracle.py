@@ -142,6 +142,16 @@ def raster_rows(inst: np.ndarray, width: int, height: int, row0: int, row1: int,
     return out
 
 
+def raster_band_list(inst: np.ndarray, width: int, height: int, bands, mode: int = 0, tile: int = 16):
+    """The listed tile bands (rows [b * tile, b * tile + tile)), one OpenMP thread per band; other rows stay zero."""
+    inst = _f32(inst).reshape(-1, 12)
+    bands = np.ascontiguousarray(bands, dtype=np.uint32)
+    out = np.zeros((height, width, 4), np.uint8)
+    lib().vko_raster_band_list(C.c_uint32(inst.shape[0]), _p(inst), C.c_uint32(width), C.c_uint32(height), C.c_uint32(tile),
+                               C.c_int(mode), C.c_uint32(bands.shape[0]), _p(bands), _p(out))
+    return out
+
+
 def raster_lines(positions, colors, pvm, width: int, height: int):
     """The opaque line layer (axis / grid of the reference viewer): (depth f32 [H,W], rgba u8 [H,W,4])."""
     pos = _f32(positions).reshape(-1, 6)

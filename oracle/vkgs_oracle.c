@@ -560,18 +560,10 @@ VKO_API void vko_raster_lines(uint32_t n_lines, const float* pos /* 2n x 3 */, c
 /* Rows outside [row0,row1) (rounded outwards to whole tile bands) are left untouched in out.
  * layer_depth / layer_rgba (both NULL, or both W*H): the opaque layer under the splats - the accumulators start from its
  * colour and a fragment is kept only if ndc.z < layer_depth (depth test LESS, no write). */
-VKO_API void vko_raster_rows_layer(uint32_t v, const float* inst, uint32_t W, uint32_t H, uint32_t tile, int mode,
-                                   uint32_t row0, uint32_t row1, const float* layer_depth, const uint8_t* layer_rgba,
-                                   uint8_t* out, float* fout) {
-  raster_splat* S = (raster_splat*)malloc((size_t)(v ? v : 1) * sizeof(raster_splat));
-#pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < (int64_t)v; ++i) raster_setup(inst + 12 * i, W, H, &S[i]);
-
-  int nband = (int)((H + tile - 1) / tile);
-  int band_lo = (int)(row0 / tile), band_hi = (int)((row1 + tile - 1) / tile);
-  if (band_hi > nband) band_hi = nband;
-#pragma omp parallel for schedule(dynamic, 1)
-  for (int band = band_lo; band < band_hi; ++band) {
+/* One tile band (rows [band * tile, band * tile + tile)) of the frame: every splat, back to front. */
+static void raster_band(const raster_splat* S, uint32_t v, uint32_t W, uint32_t H, uint32_t tile, int mode, int band,
+                        const float* layer_depth, const uint8_t* layer_rgba, uint8_t* out, float* fout) {
+  {
     int by0 = band * (int)tile, by1 = by0 + (int)tile - 1;
     if (by1 > (int)H - 1) by1 = (int)H - 1;
     size_t npx = (size_t)W * (size_t)(by1 - by0 + 1);
@@ -639,6 +631,36 @@ VKO_API void vko_raster_rows_layer(uint32_t v, const float* inst, uint32_t W, ui
       }
     free(acc);
   }
+}
+
+static raster_splat* raster_setup_all(uint32_t v, const float* inst, uint32_t W, uint32_t H) {
+  raster_splat* S = (raster_splat*)malloc((size_t)(v ? v : 1) * sizeof(raster_splat));
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)v; ++i) raster_setup(inst + 12 * i, W, H, &S[i]);
+  return S;
+}
+
+VKO_API void vko_raster_rows_layer(uint32_t v, const float* inst, uint32_t W, uint32_t H, uint32_t tile, int mode,
+                                   uint32_t row0, uint32_t row1, const float* layer_depth, const uint8_t* layer_rgba,
+                                   uint8_t* out, float* fout) {
+  raster_splat* S = raster_setup_all(v, inst, W, H);
+  int nband = (int)((H + tile - 1) / tile);
+  int band_lo = (int)(row0 / tile), band_hi = (int)((row1 + tile - 1) / tile);
+  if (band_hi > nband) band_hi = nband;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int band = band_lo; band < band_hi; ++band)
+    raster_band(S, v, W, H, tile, mode, band, layer_depth, layer_rgba, out, fout);
+  free(S);
+}
+
+/* A list of tile bands (indices in units of `tile` rows), one thread each: the stratified CPU sample of bench.py. */
+VKO_API void vko_raster_band_list(uint32_t v, const float* inst, uint32_t W, uint32_t H, uint32_t tile, int mode,
+                                  uint32_t nbands, const uint32_t* bands, uint8_t* out) {
+  raster_splat* S = raster_setup_all(v, inst, W, H);
+  int nband = (int)((H + tile - 1) / tile);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < (int)nbands; ++b)
+    if ((int)bands[b] < nband) raster_band(S, v, W, H, tile, mode, (int)bands[b], NULL, NULL, out, NULL);
   free(S);
 }
 

@@ -1,0 +1,24 @@
+#!/bin/bash
+# multi-GPU validation: usage tools/r02_mg.sh <tag> <ngpus> [c5 splats]
+tag=${1:-r02mg}; n=${2:-2}; n5=${3:-10000000}
+mkdir -p gpurun_out
+run() {  # name, args...
+  name=$1; shift
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n "$@" > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}_${name}.err
+  python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/${tag}_${name}.json").read().strip().splitlines()[-1])
+    print("${name}: value", round(d["value"], 1), d["unit"], "ms/step", round(d["ms_per_step"], 4), "e2e", round(d.get("e2e", {}).get("value", 0), 1), {k: round(v, 4) for k, v in d["stages_ms"].items()}, "u8", round(d.get("value_unorm8", 0), 1))
+    print("   ", d["config"].get("parallelism"))
+except Exception as e:
+    print("${name}: failed:", e); print(open("gpurun_out/${tag}_${name}.err").read()[-1500:])
+PY
+}
+nvidia-smi topo -m > gpurun_out/${tag}_topo.txt 2>&1
+run c2_peer --steps 100 --warmup 10 --no-cpu-baseline --gather peer
+run c2_nccl --steps 100 --warmup 10 --no-cpu-baseline --gather nccl
+run c4_peer --config c4 --steps 45 --warmup 5 --gather peer
+run c4_nccl --config c4 --steps 45 --warmup 5 --gather nccl
+run c5_peer --config c5 --steps 20 --warmup 3 --gather peer --n-splats $n5
+run c5_nccl --config c5 --steps 20 --warmup 3 --gather nccl --n-splats $n5
