@@ -323,6 +323,9 @@ def main():
     ap.add_argument("--blend", default="fp32", choices=["fp32", "unorm8"], help="blend mode of the headline `value`")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="how finished images reach rank 0 (N > 1)")
     ap.add_argument("--n-splats", type=int, default=0, help="override the scene size (experiments)")
+    ap.add_argument("--band-cull", default="shared", choices=["shared", "replicated"],
+                    help="c5: the cull shared out over the ranks (vkgsb_group_*: each rank tests 1/N of the splats against "
+                         "every band and writes the bands' bits into their GPUs) or repeated over the whole scene by every rank")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.n_splats:
@@ -395,16 +398,16 @@ def run_views(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
     sptr = stream.cuda_stream
     img_bytes = W_ * H_ * 4
     if args.config == "c4":
-        # strong scaling of one 360-view orbit: rank g renders its contiguous block of the views (dist.shard_views);
-        # --steps bounds the views per rank so that a default run stays short
-        mine = list(vdist.shard_views(cfg["n_views"], rank, world))
+        # strong scaling of one 360-view orbit: the views are dealt round-robin (dist.deal_views: neighbouring views cost
+        # about the same, so every rank gets the same mix); --steps bounds the views per rank so that a default run
+        # stays short
+        mine = list(vdist.deal_views(cfg["n_views"], rank, world))
         K = min(K, len(mine))
         views = [mine[i % len(mine)] for i in range(max(K, W))]
-        total_views = sum(min(args.steps, len(vdist.shard_views(cfg["n_views"], g, world))) for g in range(world))
+        total_views = sum(min(args.steps, len(vdist.deal_views(cfg["n_views"], g, world))) for g in range(world))
     else:
-        # weak scaling: K frames per rank; rank g's block of the orbit starts at view g * K (contiguous blocks, the way
-        # dist.shard_views deals them)
-        views = [rank * K + i for i in range(max(K, W))]
+        # weak scaling: K frames per rank, dealt round-robin like dist.deal_views: at step i rank g renders view i * world + g
+        views = [i * world + rank for i in range(max(K, W))]
         total_views = world * K
     cams = [vkgs_b200.camera_block(*view_camera(cfg, v)) for v in views]
     if world > 1 and args.gather == "peer":
@@ -532,9 +535,9 @@ def run_views(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"], "blend": name[head], "visible_mean": V_mean, "pairs_mean": S["D"],
-                   "parallelism": (f"views sharded over {world} GPU(s) in contiguous blocks, scene replicated, " + deliver.name)
+                   "parallelism": (f"views dealt round-robin over {world} GPU(s), scene replicated, " + deliver.name)
                    if world > 1 else "single GPU",
-                   "l2": f"inputs larger than L2: {144 * cfg['n_splats'] / 1e6:.0f} MB resident scene streamed per frame, "
+                   "l2": f"inputs larger than L2: {144 * cfg['n_splats'] / 1e6:.0f} MB resident scene, its centres and visible payload lines streamed per frame, "
                          "a different camera each step",
                    "pair_overflow": S["overflow"]},
         "stages_ms": stage,
@@ -594,7 +597,15 @@ def run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
         deliver = None
         frame = torch.zeros((H_, W_, 4), dtype=torch.uint8, device=dev)
         gathered = [torch.empty_like(frame) for _ in range(world)] if (world > 1 and rank == 0) else None
-    r.set_band(edges[rank], edges[rank + 1]) if world > 1 else r.set_band(0, 0)
+    grouped = world > 1 and args.band_cull == "shared"
+    if grouped:
+        handles = [None] * world
+        dist.all_gather_object(handles, r.group_export())
+        r.group_join(rank, world, handles, edges)          # also sets this rank's band
+    elif world > 1:
+        r.set_band(edges[rank], edges[rank + 1])
+    else:
+        r.set_band(0, 0)
 
     def step(i):
         r.set_camera(block=cams[i % len(cams)])
@@ -634,11 +645,17 @@ def run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
         r.draw_device(stream=sptr)
         if i >= 3:
             s = r.stats()
-            for k in ("ms_project", "ms_sort", "ms_bin", "ms_blend", "ms_total"):
+            for k in ("ms_cull", "ms_project", "ms_sort", "ms_bin", "ms_blend", "ms_total"):
                 acc[k[3:]] = acc.get(k[3:], 0.0) + s[k] / 8
             vis.append(s["visible_point_count"])
     r.set_option(L.OPT_STAGE_TIMING, 0)
     slowest = vdist.max_over_ranks(acc["total"], dev)
+    per_rank = [None] * world
+    if world > 1:
+        dist.all_gather_object(per_rank, dict(acc, visible=float(np.mean(vis))))
+    if grouped:
+        barrier()
+        r.group_leave()
     if deliver is not None:
         barrier()
         deliver.close()
@@ -650,11 +667,13 @@ def run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
         "data": "synthetic",
         "config": {"workload": cfg["workload"], "blend": args.blend, "band_edges": edges,
                    "parallelism": (f"{world} screen bands on {world} GPU(s), scene replicated, band edges balanced on the row "
-                                   "histogram; " + (PeerWrite.name if deliver is not None else "bands gathered to rank 0 (NCCL)"))
+                                   "histogram; cull " + ("shared out over the ranks, each band's visibility bits written into its GPU "
+                                                         "over NVLink (no collective); " if grouped else "repeated by every rank; ") + (PeerWrite.name if deliver is not None else "bands gathered to rank 0 (NCCL)"))
                    if world > 1 else "single GPU, whole frame",
-                   "l2": f"inputs larger than L2: {144 * cfg['n_splats'] / 1e6:.0f} MB resident scene streamed per frame",
+                   "l2": f"inputs larger than L2: {144 * cfg['n_splats'] / 1e6:.0f} MB resident scene, its centres and visible payload lines streamed per frame",
                    "rank0_visible_mean": float(np.mean(vis))},
         "stages_ms": acc, "slowest_band_stages_ms_total": slowest,
+        "bands": [{k: round(v, 4) for k, v in b.items()} for b in per_rank] if world > 1 else None,
         "gpu_launches": KERNELS_PER_FRAME * K, "clocks": clocks,
     }
 

@@ -195,6 +195,24 @@ VKGSB_API int vkgsb_shared_close(int device, void* d_ptr);
 VKGSB_API int vkgsb_shared_read(int device, const void* d_ptr, size_t offset, size_t bytes, void* host_dst);
 VKGSB_API int vkgsb_shared_destroy(int device, void* d_ptr);
 
+/* Band group (BASELINE configs[4]): W renderers - one per GPU, normally one per process - draw the W screen
+ * bands of the same frames; member g draws rows [edges[g], edges[g + 1]) (VKGSB_OPT_BAND_Y0 / Y1 are set by the join).
+ * The cull, which every member would otherwise repeat over the whole scene, is shared out: member j tests the splats of
+ * its 1/W share against the frustum and against every band's footprint bound and writes each band's visibility bits
+ * straight into that band's member over NVLink (peer mappings of one allocation per renderer, CUDA IPC); members
+ * hand-shake through frame-numbered flags in each other's memory, no collective and no host round trip.  Contract: all
+ * members hold the same scene and were created with the same max_splats; every member issues the same sequence of frames
+ * (same camera, viewport, options) after the join; a member that does not makes the others' frames give up after ~2 s,
+ * reported by vkgsb_sync.  Frames are bit-identical to the same rows of the ungrouped full frame.
+ * vkgsb_group_export: this renderer's 64-byte handle; vkgsb_group_join: handles = world x 64 bytes in rank order (the own
+ * entry is ignored), edges = world + 1 rows; vkgsb_group_join_local: the members live in this process (tests, one
+ * process driving several GPUs). */
+VKGSB_API int vkgsb_group_export(vkgsb_renderer* r, uint8_t handle[64]);
+VKGSB_API int vkgsb_group_join(vkgsb_renderer* r, uint32_t rank, uint32_t world, const uint8_t* handles,
+                               const uint32_t* edges);
+VKGSB_API int vkgsb_group_join_local(vkgsb_renderer* const* members, uint32_t world, const uint32_t* edges);
+VKGSB_API int vkgsb_group_leave(vkgsb_renderer* r);
+
 /* Parity taps (test / debugging): state of the last drawn frame, copied to host.
  * read_sorted: keys/ids in sorted (far -> near) order = SplatStorage.key / .index after vrdx (engine.cc:1218-1219).
  * read_instances: 12 floats per visible splat in sorted order = SplatStorage.instance (projection.comp:177-179).

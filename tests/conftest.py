@@ -4,6 +4,10 @@ import sys
 import numpy as np
 import pytest
 
+# band groups of several renderers in ONE process (tests/test_gpu_group.py) wait for each other on the device: every
+# stream needs its own hardware queue, or a waiting kernel can sit in front of the kernel it waits for
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -26,7 +26,7 @@ def measure(r, cams, frames=40, warm=5):
         r.draw_device()
         if i >= warm:
             s = r.stats()
-            for k in ("ms_project", "ms_sort", "ms_bin", "ms_blend", "ms_total"):
+            for k in ("ms_cull", "ms_project", "ms_sort", "ms_bin", "ms_blend", "ms_total"):
                 acc[k] = acc.get(k, 0.0) + s[k] / frames
             vis.append(s["visible_point_count"]); pairs.append(s["pair_count"])
             assert s["pair_overflow"] == 0
@@ -64,17 +64,17 @@ def main():
             res = measure(r, orbit_cams(w, h, 45, r=1.5, phi_deg=70.0))   # one of 8 GPUs' share of a 360-view orbit
             print(json.dumps({"config": "C4 bicycle-shaped 6,131,954 splats, 3840x2160, 45 of 360 orbit views", **res}))
     if "c5" in which:
-        w, h = 1600, 900
+        w, h = 3840, 2160
         rows = synth.scene_large(n5)
-        with vkgs_b200.Renderer(max_splats=n5, max_width=w, max_height=h, max_pairs=256_000_000) as r:
+        with vkgs_b200.Renderer(max_splats=n5, max_width=w, max_height=h, max_pairs=400_000_000) as r:
             r.upload_splats(rows); del rows
             r.set_viewport(w, h)
             cams = orbit_cams(w, h, 8, r=6.0, phi_deg=70.0)
             res = measure(r, cams, frames=16, warm=3)
-            print(json.dumps({"config": f"C5 {n5:,} splats, 1600x900, whole frame on one GPU", **res}))
+            print(json.dumps({"config": f"C5 {n5:,} splats, 3840x2160, whole frame on one GPU", **res}))
             r.set_band(4 * h // 8, 5 * h // 8)
             res = measure(r, cams, frames=16, warm=3)
-            print(json.dumps({"config": f"C5 {n5:,} splats, 1600x900, band 5 of 8 (what one GPU of 8 runs: the cull drops what cannot reach the band)", **res}))
+            print(json.dumps({"config": f"C5 {n5:,} splats, 3840x2160, band 5 of 8 (what one GPU of 8 runs: the cull drops what cannot reach the band)", **res}))
 
 
 if __name__ == "__main__":

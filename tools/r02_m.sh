@@ -1,0 +1,20 @@
+#!/bin/bash
+tag=${1:-r02m}
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q -k "not c5_50m" > gpurun_out/${tag}_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
+tail -8 gpurun_out/${tag}_pytest.log
+for v in main cull_s2b4 cull_s3b3 cull_s2b3; do
+  lib=""
+  [ "$v" != "main" ] && lib="$PWD/vkgs_b200/lib/libvkgsb_${v}.so"
+  VKGSB_LIB=$lib timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/${tag}_${v}.json 2> gpurun_out/${tag}_${v}.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${tag}_${v}.json"))
+    print("${v}: fps", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), {k: round(v, 4) for k, v in d["stages_ms"].items()}, "roof", round(d["roofline"]["frac"], 3), "u8", round(d.get("value_unorm8", 0), 1))
+except Exception as e:
+    print("${v}: bench failed:", e); print(open("gpurun_out/${tag}_${v}.err").read()[-800:])
+PY
+done
+timeout 900 python tools/config_times.py c5 > gpurun_out/${tag}_c5.jsonl 2> gpurun_out/${tag}_c5.err; cat gpurun_out/${tag}_c5.jsonl; tail -3 gpurun_out/${tag}_c5.err

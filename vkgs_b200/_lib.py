@@ -64,6 +64,10 @@ SIGNATURES = {
     "vkgsb_read_scene": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "vkgsb_sort_storage_bytes": (C.c_int, [C.c_uint32, C.POINTER(C.c_size_t)]),
     "vkgsb_sort_key_value_indirect": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
+    "vkgsb_group_export": (C.c_int, [_P, _P]),
+    "vkgsb_group_join": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),
+    "vkgsb_group_join_local": (C.c_int, [C.POINTER(_P), C.c_uint32, _P]),
+    "vkgsb_group_leave": (C.c_int, [_P]),
     "vkgsb_shared_create": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P), _P]),
     "vkgsb_shared_open": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "vkgsb_shared_close": (C.c_int, [C.c_int, _P]),

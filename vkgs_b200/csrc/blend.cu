@@ -165,14 +165,18 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
     return e;
   };
   uint32_t nfrag = 0;
-  // alpha of entry e at pixel k of this lane; false when the pixel is outside the +-3 sigma square / behind the layer
-  auto fragment = [&](const Entry& e, int k, float* al) {
+  // alpha of entry e at pixel k of this lane - 0 when the pixel is not `live`, outside the +-3 sigma square or behind the
+  // layer.  Branch-free: a zero alpha makes every blend step below an exact no-op, and one divergent region per pixel
+  // cost more than the arithmetic it skipped.  exp(-d/2) = 2^(-d * log2(e) / 2) with the ftz form of ex2 (__expf's
+  // own instruction without its denormal-range rescaling: alphas below 2^-126 become 0).
+  auto alpha = [&](const Entry& e, int k, bool live) {
     const float px = fmaf(e.q0.x, flx, fmaf(e.q0.y, fly[k], e.bx));
     const float py = fmaf(e.q0.z, flx, fmaf(e.q0.w, fly[k], e.by));
-    if (!(fabsf(px) <= 3.f && fabsf(py) <= 3.f && (!LAYER || e.z < ldepth[k]))) return false;
-    *al = __saturatef(e.q2.y * __expf(-0.5f * fmaf(py, py, px * px)));
-    if (COUNT) ++nfrag;
-    return true;
+    const bool cov = live && fabsf(px) <= 3.f && fabsf(py) <= 3.f && (!LAYER || e.z < ldepth[k]);
+    float ex;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-0.72134752044448170368f * fmaf(py, py, px * px)));
+    if (COUNT && cov) ++nfrag;
+    return cov ? __saturatef(e.q2.y * ex) : 0.f;
   };
   // the frame's destination travels in the parameter block, so one recorded graph serves every destination
   uint32_t* img = reinterpret_cast<uint32_t*>(fpp->dst_image ? reinterpret_cast<uint8_t*>(fpp->dst_image) : image);
@@ -207,16 +211,14 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
             const Entry e = entry(j);
 #pragma unroll
             for (int k = 0; k < kPix; ++k) {
-              float al;
-              if (!done[k] && fragment(e, k, &al)) {
-                const float w = al * T[k];
-                cr[k] = fmaf(e.q1.z, w, cr[k]);
-                cg[k] = fmaf(e.q1.w, w, cg[k]);
-                cb[k] = fmaf(e.q2.x, w, cb[k]);
-                ca[k] = fmaf(al, w, ca[k]);
-                T[k] -= w;
-                done[k] = T[k] < kTransmittanceCut;
-              }
+              const float al = alpha(e, k, !done[k]);
+              const float w = al * T[k];
+              cr[k] = fmaf(e.q1.z, w, cr[k]);
+              cg[k] = fmaf(e.q1.w, w, cg[k]);
+              cb[k] = fmaf(e.q2.x, w, cb[k]);
+              ca[k] = fmaf(al, w, ca[k]);
+              T[k] -= w;
+              done[k] = done[k] || T[k] < kTransmittanceCut;
             }
             if (__all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3])) {
               warp_done = true;
@@ -245,10 +247,17 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
     // the far end of the list, from the real background, and is exact).
     float T[kPix];
     uint32_t cut[kPix];
+    // A pixel is FINAL once its own bracket has been certified; its value then never depends on what the other pixels of
+    // the warp need (a later, deeper attempt only serves the pixels still open), so a pixel's result is a function of
+    // its own splat list alone - bands, regions and groups all give the same bits.
+    uint32_t fin[kPix];
+    bool isfin[kPix];
 #pragma unroll
     for (int k = 0; k < kPix; ++k) {
       T[k] = 1.f;
       cut[k] = kNoCut;
+      fin[k] = lrgba[k] | 0xff000000u;
+      isfin[k] = !inside[k];
     }
     const bool any_inside = __any_sync(0xffffffffu, inside[0] || inside[1] || inside[2] || inside[3]);
     bool wfinal = !any_inside || range.y == range.x;  // warp-uniform: this warp's pixels are written
@@ -275,7 +284,7 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
       bool done[kPix];
 #pragma unroll
       for (int k = 0; k < kPix; ++k) {
-        done[k] = !inside[k] || T[k] < tau;
+        done[k] = isfin[k] || T[k] < tau;
         if (!done[k]) cut[k] = kNoCut;  // set again when it crosses this attempt's (lower) tau
       }
       bool warp_done = wfinal || wnext >= range.y || __all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3]);
@@ -303,13 +312,11 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
                 const Entry e = entry(j);
 #pragma unroll
                 for (int k = 0; k < kPix; ++k) {
-                  float al;
-                  if (!done[k] && fragment(e, k, &al)) {
-                    T[k] = __fmul_rn(T[k], __fsub_rn(1.f, al));
-                    if (T[k] < tau) {
-                      done[k] = true;
-                      cut[k] = b0 + j;
-                    }
+                  const float al = alpha(e, k, !done[k]);
+                  T[k] = __fmul_rn(T[k], __fsub_rn(1.f, al));
+                  if (!done[k] && T[k] < tau) {
+                    done[k] = true;
+                    cut[k] = b0 + j;
                   }
                 }
                 if (__all_sync(0xffffffffu, done[0] && done[1] && done[2] && done[3])) {
@@ -342,7 +349,7 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
       // the warp's deepest start; entries behind it are skipped without a look
       uint32_t wcut = 0;
 #pragma unroll
-      for (int k = 0; k < kPix; ++k) wcut = max(wcut, inside[k] ? cut[k] : 0u);
+      for (int k = 0; k < kPix; ++k) wcut = max(wcut, isfin[k] ? 0u : cut[k]);
       wcut = __reduce_max_sync(0xffffffffu, wcut);
       // warp-uniform: in every channel of every pixel the ends are at most 1 apart.  A ROP step never widens the gap
       // (|F(q + g) - F(q)| <= g for 0 <= a <= 1), so from here on one end is enough: the other stays within 1 of it.
@@ -366,34 +373,30 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
               if (!met) {
 #pragma unroll
                 for (int k = 0; k < kPix; ++k) {
-                  float al;
-                  if (b0 + j <= cut[k] && fragment(e, k, &al)) {
-                    const float om = __fsub_rn(1.f, al), a255 = __fmul_rn(255.f, al);
+                  const float al = alpha(e, k, !isfin[k] && b0 + j <= cut[k]);  // 0 before the pixel's own start: a no-op
+                  const float om = __fsub_rn(1.f, al), a255 = __fmul_rn(255.f, al);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                      const float sc = c < 3 ? s255[c < 3 ? c : 0] : a255;
-                      lo[k][c] = rint255(fmaf(sc, al, __fmul_rn(lo[k][c], om)));
-                      hi[k][c] = rint255(fmaf(sc, al, __fmul_rn(hi[k][c], om)));
-                    }
+                  for (int c = 0; c < 4; ++c) {
+                    const float sc = c < 3 ? s255[c < 3 ? c : 0] : a255;
+                    lo[k][c] = rint255(fmaf(sc, al, __fmul_rn(lo[k][c], om)));
+                    hi[k][c] = rint255(fmaf(sc, al, __fmul_rn(hi[k][c], om)));
                   }
                 }
                 bool close = true;  // a pixel still waiting for its (nearer) cut holds 0 / 255: not close
 #pragma unroll
                 for (int k = 0; k < kPix; ++k)
 #pragma unroll
-                  for (int c = 0; c < 4; ++c) close = close && (!inside[k] || hi[k][c] - lo[k][c] <= 1.f);
+                  for (int c = 0; c < 4; ++c) close = close && (isfin[k] || hi[k][c] - lo[k][c] <= 1.f);
                 met = __all_sync(0xffffffffu, close);
               } else {
 #pragma unroll
                 for (int k = 0; k < kPix; ++k) {
-                  float al;
-                  if (fragment(e, k, &al)) {
-                    const float om = __fsub_rn(1.f, al), a255 = __fmul_rn(255.f, al);
+                  const float al = alpha(e, k, true);
+                  const float om = __fsub_rn(1.f, al), a255 = __fmul_rn(255.f, al);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                      const float sc = c < 3 ? s255[c < 3 ? c : 0] : a255;
-                      lo[k][c] = rint255(fmaf(sc, al, __fmul_rn(lo[k][c], om)));
-                    }
+                  for (int c = 0; c < 4; ++c) {
+                    const float sc = c < 3 ? s255[c < 3 ? c : 0] : a255;
+                    lo[k][c] = rint255(fmaf(sc, al, __fmul_rn(lo[k][c], om)));
                   }
                 }
               }
@@ -402,26 +405,35 @@ k_blend(const FrameParams* __restrict__ fpp, Control* __restrict__ ctrl, const u
         }
         if (b0 == range.x) break;
       }
-      // ---- the certificate: ends at most 1 apart everywhere -> lo is within 1/255 of the exact recurrence's result
-      //      (equal to it where the ends met).  Otherwise the warp tries again from a deeper cut.
+      // ---- the certificate, per pixel: ends at most 1 apart in every channel -> lo is within 1/255 of the exact
+      //      recurrence's result (equal to it where the ends met) and the pixel is final.  A warp with pixels still
+      //      open tries again from a deeper cut - for those pixels only.
       if (!wfinal) {
-        bool close = true;
-        if (!met) {
+        bool open = false;
 #pragma unroll
-          for (int k = 0; k < kPix; ++k)
+        for (int k = 0; k < kPix; ++k) {
+          if (isfin[k]) continue;
+          bool close = true;
+          if (!met) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) close = close && (!inside[k] || hi[k][c] - lo[k][c] <= 1.f);
-          close = __all_sync(0xffffffffu, close);
+            for (int c = 0; c < 4; ++c) close = close && hi[k][c] - lo[k][c] <= 1.f;
+          }
+          if (close) {
+            fin[k] = clamp255(lo[k][0]) | (clamp255(lo[k][1]) << 8) | (clamp255(lo[k][2]) << 16) | (clamp255(lo[k][3]) << 24);
+            isfin[k] = true;
+          } else {
+            open = true;
+          }
         }
-        if (close) {
+        if (__any_sync(0xffffffffu, open)) {
+          if (lane == 0) atomicAdd(&ctrl->blend_retries, 1u);
+        } else {
 #pragma unroll
           for (int k = 0; k < kPix; ++k)
             if (inside[k])
               img[static_cast<size_t>(y_first + 2 * k) * width + x] =
-                  pack_pixel(clamp255(lo[k][0]), clamp255(lo[k][1]), clamp255(lo[k][2]), clamp255(lo[k][3]), bgra);
+                  pack_pixel(fin[k] & 255u, (fin[k] >> 8) & 255u, (fin[k] >> 16) & 255u, fin[k] >> 24, bgra);
           wfinal = true;
-        } else if (lane == 0) {
-          atomicAdd(&ctrl->blend_retries, 1u);
         }
       }
       __syncthreads();  // everyone has read s_redo (staging) before it changes

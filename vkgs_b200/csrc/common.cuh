@@ -73,7 +73,7 @@ struct FrameParams {
   //   ey^2 <= bc_a * (bc_p + x_ndc^2 + y_ndc^2) * lambda_max(Sigma) / w^2 + bc_b
   float bc_a, bc_b, bc_p;
   float unorm8_cut;  // VKGSB_BLEND_UNORM8: transmittance below which the first attempt starts its back-to-front walk
-  uint32_t pad4;
+  uint32_t epoch;    // frame number (band groups: the value of the hand-shake flags, project.cu)
   unsigned long long dst_image;  // where the blend stage writes this frame's pixels: the renderer's own image, or the
                                  // caller's device destination (possibly another GPU's memory, mapped over NVLink)
 };

@@ -41,9 +41,32 @@ struct CullIndexLayout {
 };
 CullIndexLayout cull_index_layout(uint32_t max_splats);
 void project_configure();  // once per device: opt in to > 48 KB dynamic shared memory
+// ---- band group: the cull of a frame shared out over the W renderers that each draw one screen band of it ------------
+constexpr int kMaxGroup = 16;
+// Flags of one member, written by the others over NVLink (system-scope release / acquire); epochs are frame numbers.
+struct GroupFlags {
+  unsigned long long arrive[2][kMaxGroup];  // [parity][source]: source's share of that frame's cull has landed here
+  unsigned long long consumed[2];           // [parity]: this member's k_project of that frame has read its cull index
+  unsigned int timeout;                     // a wait gave up (a member did not issue the frame): the frame is garbage
+};
+struct GroupParams {
+  uint32_t rank, world;
+  uint32_t tile0, tile1;             // this member's share of the scene: CTA tiles [tile0, tile1) of 2048 splats
+  uint32_t edges[kMaxGroup + 1];     // band g = rows [edges[g], edges[g + 1])
+  CullIndex peer[kMaxGroup];         // member g's cull index of this parity (own entry: local memory)
+  GroupFlags* flags[kMaxGroup];      // member g's flags
+};
+// member `rank`'s share: every band's visibility bits for its splats, written into that band's member
+void launch_cull_group(const Scene& scene, const FrameParams* d_fp, const GroupParams& gp, int parity, cudaStream_t stream);
+// destination side: wait for every member's share, then build the upper levels of the count tree (zero on entry)
+void launch_group_tree(const FrameParams* d_fp, const GroupParams& gp, int parity, uint32_t n, cudaStream_t stream);
+// after k_project: this member's cull index of the frame may be overwritten
+void launch_group_consumed(const FrameParams* d_fp, GroupFlags* own, int parity, cudaStream_t stream);
+
 // k_cull: the scene's centres -> cull index `ix` (its upper levels zero on entry).  Reads only the parameter block and
 // the scene, so a frame's cull may run while the previous frame is still in its later stages.
-void launch_cull(const Scene& scene, const FrameParams* d_fp, const CullIndex& ix, cudaStream_t stream);
+// band_mode: FrameParams::flags has kFlagBandCull (the launch also stages the splats' lambda_max)
+void launch_cull(const Scene& scene, const FrameParams* d_fp, const CullIndex& ix, bool band_mode, cudaStream_t stream);
 // k_project.  d_rrec: 3 x float4 raster record per visible slot; d_inst: 12-float instance record (written only when
 // FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control and writes
 // Control::visible_count.

@@ -81,6 +81,17 @@ struct vkgsb_renderer {
   size_t cull_tree_bytes = 0;
   cudaStream_t cull_stream = nullptr;
   cudaEvent_t cull_done[2] = {nullptr, nullptr};
+  // band group (vkgsb_group_*): mask + tile counts of both parities and the hand-shake flags live in ONE allocation the
+  // other members map; `gp[p]` holds every member's pointers for parity p
+  uint8_t* group_block = nullptr;
+  size_t group_off_mask[2] = {0, 0}, group_off_cnt[2] = {0, 0}, group_off_flags = 0, group_bytes = 0;
+  GroupFlags* group_flags = nullptr;
+  bool grouped = false;
+  GroupParams gp[2]{};
+  void* group_peer_base[kMaxGroup] = {nullptr};
+  bool group_peer_ipc[kMaxGroup] = {false};
+  uint64_t group_epoch = 0;  // frames drawn as a member; parity of a group frame = its epoch & 1 (the same on every member)
+  int last_parity = 0;
   uint2* ranges = nullptr;
   FrameParams* d_fp[2] = {nullptr, nullptr};
   uint8_t* image = nullptr;
@@ -357,7 +368,18 @@ int record_cull(vkgsb_renderer* r, int p, cudaStream_t s, bool clear = true) {
   const uint32_t n = r->scene_n.load();
   Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, n};
   if (clear) CU_TRY(cudaMemsetAsync(r->cull_tree[p], 0, r->cull_tree_bytes, s));
-  launch_cull(sc, r->d_fp[p], r->cull[p], s);
+  if (r->grouped) {
+    // this member's share of the scene against every band, written into the bands' members; then wait for the others'
+    // shares of this band and build the count tree
+    GroupParams gp = r->gp[p];
+    const uint32_t nct = (n + 2047u) / 2048u;
+    gp.tile0 = static_cast<uint32_t>(static_cast<uint64_t>(nct) * gp.rank / gp.world);
+    gp.tile1 = static_cast<uint32_t>(static_cast<uint64_t>(nct) * (gp.rank + 1) / gp.world);
+    launch_cull_group(sc, r->d_fp[p], gp, p, s);
+    launch_group_tree(r->d_fp[p], gp, p, n, s);
+  } else {
+    launch_cull(sc, r->d_fp[p], r->cull[p], (r->h_fp.flags & kFlagBandCull) != 0u, s);
+  }
   CU_TRY(cudaGetLastError());
   return VKGSB_OK;
 }
@@ -380,6 +402,7 @@ int record_stages(vkgsb_renderer* r, int p, cudaStream_t s, bool timed) {
   FrameParams* d_fp = r->d_fp[p];
   // the depth sort runs an odd number of passes: its input goes to the ping-pong side, its result lands in keys / slots
   launch_project(sc, d_fp, r->ctrl, r->cull[p], r->keys_alt, r->rrec, r->bin_rect, r->inst, r->n_lines ? r->zndc : nullptr, s);
+  if (r->grouped) launch_group_consumed(d_fp, r->group_flags, p, s);  // the others may write the next frame of this parity
   if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
   SortArgs depth{};
   depth.d_count = &r->ctrl->visible_count;
@@ -418,10 +441,13 @@ int run_frame(vkgsb_renderer* r, cudaStream_t s, void* direct_dst = nullptr) {
   // the work buffers are shared by all frames: a frame on another stream than the last one waits for it
   if (r->frame_counter && s != r->last_stream) CU_TRY(cudaStreamWaitEvent(s, r->flight[r->frame_counter & 3], 0));
   fill_params(r);
-  r->h_fp.pad4 = 0u;
   r->h_fp.dst_image = reinterpret_cast<unsigned long long>(direct_dst);
   const uint64_t f = r->frame_counter + 1;  // this frame
-  const int p = static_cast<int>(f & 1);
+  // a group frame's parity is the same on every member (they write into each other's parity buffers)
+  if (r->grouped) r->group_epoch++;
+  const int p = static_cast<int>((r->grouped ? r->group_epoch : f) & 1);
+  r->h_fp.epoch = static_cast<uint32_t>(r->group_epoch);
+  r->last_parity = p;
   if (r->stage_timing) {
     // eager, everything on the frame's stream, events between the stages
     k_set_params<<<1, 32, 0, s>>>(r->h_fp, r->d_fp[p]);
@@ -560,13 +586,29 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   r->ctrl = reinterpret_cast<Control*>(r->zero_region);
   r->ranges = reinterpret_cast<uint2*>(r->zero_region + ctrl_bytes);
   r->cull_tree_bytes = ((static_cast<size_t>(cl.na) + cl.nb + cl.nc + 63) & ~size_t(63)) * 4;
+  {
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    size_t o = 0;
+    for (int p = 0; p < 2; ++p) {
+      r->group_off_mask[p] = o;
+      o += up(static_cast<size_t>(cl.tiles) * 8 * 4);
+      r->group_off_cnt[p] = o;
+      o += up(static_cast<size_t>(cl.tiles) * 4);
+    }
+    r->group_off_flags = o;
+    o += up(sizeof(GroupFlags));
+    r->group_bytes = o;
+    ALLOC(r->group_block, r->group_bytes);
+    if ((e = cudaMemset(r->group_block + r->group_off_flags, 0, sizeof(GroupFlags))) != cudaSuccess) return bail("cudaMemset", e);
+    r->group_flags = reinterpret_cast<GroupFlags*>(r->group_block + r->group_off_flags);
+  }
   for (int p = 0; p < 2; ++p) {
     ALLOC(r->cull_tree[p], r->cull_tree_bytes);
     r->cull[p].lvl_a = r->cull_tree[p];
     r->cull[p].lvl_b = r->cull[p].lvl_a + cl.na;
     r->cull[p].lvl_c = r->cull[p].lvl_b + cl.nb;
-    ALLOC(r->cull[p].mask, static_cast<size_t>(cl.tiles) * 8 * 4);
-    ALLOC(r->cull[p].tile_cnt, static_cast<size_t>(cl.tiles) * 4);
+    r->cull[p].mask = reinterpret_cast<uint32_t*>(r->group_block + r->group_off_mask[p]);
+    r->cull[p].tile_cnt = reinterpret_cast<uint32_t*>(r->group_block + r->group_off_cnt[p]);
     ALLOC(r->d_fp[p], sizeof(FrameParams));
   }
   ALLOC(r->image, static_cast<size_t>(r->max_width) * r->max_height * 4);
@@ -602,12 +644,13 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   }
   cudaSetDevice(r->device);
   if (r->stream) drain_frames(r);
+  if (r->grouped) vkgsb_group_leave(r);
   if (r->load_stream) cudaStreamSynchronize(r->load_stream);
   for (cudaGraphExec_t g : {r->graph_cull[0], r->graph_cull[1], r->graph_main[0], r->graph_main[1]})
     if (g) cudaGraphExecDestroy(g);
   void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
                  r->vis_id, r->inst, r->rrec, r->bin_rect, r->bin_slots, r->bin.tile_pairs, r->bin.tile_item, r->bin.tile_bin, r->bin.bin_total,
-                 r->lookback_depth, r->zero_region, r->cull[0].mask, r->cull[0].tile_cnt, r->cull[1].mask, r->cull[1].tile_cnt,
+                 r->lookback_depth, r->zero_region, r->group_block,
                  r->cull_tree[0], r->cull_tree[1], r->d_fp[0], r->d_fp[1], r->image, r->stage[0], r->stage[1], r->d_offsets, r->d_rows[0],
                  r->d_rows[1], r->line_pos, r->line_col, r->zndc, r->layer};
   for (void* p : dev)
@@ -834,6 +877,11 @@ int vkgsb_sync(vkgsb_renderer* r) {
   if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
   if (set_device(r)) return VKGSB_ERR_CUDA;
   CU_TRY(drain_frames(r));
+  if (r->grouped) {
+    unsigned int t = 0;
+    CU_TRY(cudaMemcpy(&t, &r->group_flags->timeout, sizeof(t), cudaMemcpyDeviceToHost));
+    if (t) return fail(VKGSB_ERR_CUDA, "band group: a member did not deliver its share of the cull in time (were all members' frames issued?)");
+  }
   return VKGSB_OK;
 }
 
@@ -896,7 +944,7 @@ int vkgsb_read_sorted(vkgsb_renderer* r, uint32_t* keys, uint32_t* ids, uint32_t
   }
   if (ids) {
     // slots_alt is free between frames: gather ids there; the ids by slot come from the frame's cull index
-    launch_expand_ids(r->cull[r->frame_counter & 1], r->scene_n.load(), r->vis_id, r->stream);
+    launch_expand_ids(r->cull[r->last_parity], r->scene_n.load(), r->vis_id, r->stream);
     launch_gather_sorted(r->ctrl, r->slots, r->vis_id, r->inst, v, r->slots_alt, nullptr, r->stream);
     CU_TRY(cudaStreamSynchronize(r->stream));
     CU_TRY(cudaMemcpy(ids, r->slots_alt, v * 4ull, cudaMemcpyDeviceToHost));
@@ -967,6 +1015,107 @@ int vkgsb_read_scene(vkgsb_renderer* r, float* pos, float* cov, float* opacity, 
   if (sh && e == cudaSuccess) e = cudaMemcpy(sh, ds, n * 96ull, cudaMemcpyDeviceToHost);
   cudaFree(dp); cudaFree(dc); cudaFree(dop); cudaFree(ds);
   CU_TRY(e);
+  return VKGSB_OK;
+}
+
+// ---- band group ----------------------------------------------------------------------------------------------------------
+static int group_setup(vkgsb_renderer* r, uint32_t rank, uint32_t world, void* const* bases, const bool* ipc,
+                       const uint32_t* edges) {
+  if (world < 2 || world > static_cast<uint32_t>(kMaxGroup) || rank >= world) return fail(VKGSB_ERR_INVALID, "bad group size / rank");
+  for (uint32_t g = 0; g < world; ++g)
+    if (edges[g] > edges[g + 1]) return fail(VKGSB_ERR_INVALID, "band edges must be non-decreasing");
+  std::lock_guard<std::mutex> g(r->draw_mutex);
+  CU_TRY(cudaDeviceSynchronize());
+  for (int p = 0; p < 2; ++p) {
+    GroupParams& gp = r->gp[p];
+    gp = GroupParams{};
+    gp.rank = rank;
+    gp.world = world;
+    for (uint32_t i = 0; i <= world; ++i) gp.edges[i] = edges[i];
+    for (uint32_t m = 0; m < world; ++m) {
+      uint8_t* base = m == rank ? r->group_block : static_cast<uint8_t*>(bases[m]);
+      gp.peer[m] = m == rank ? r->cull[p] : CullIndex{};
+      gp.peer[m].mask = reinterpret_cast<uint32_t*>(base + r->group_off_mask[p]);       // every member was created with the
+      gp.peer[m].tile_cnt = reinterpret_cast<uint32_t*>(base + r->group_off_cnt[p]);    // same max_splats: same layout
+      gp.flags[m] = reinterpret_cast<GroupFlags*>(base + r->group_off_flags);
+    }
+  }
+  for (uint32_t m = 0; m < world; ++m) {
+    r->group_peer_base[m] = m == rank ? nullptr : bases[m];
+    r->group_peer_ipc[m] = m != rank && ipc[m];
+  }
+  CU_TRY(cudaMemset(r->group_flags, 0, sizeof(GroupFlags)));
+  r->group_epoch = 0;
+  r->band_y0 = edges[rank];
+  r->band_y1 = edges[rank + 1];
+  r->grouped = true;
+  invalidate_graph(r);
+  return VKGSB_OK;
+}
+
+int vkgsb_group_export(vkgsb_renderer* r, uint8_t handle[64]) {
+  if (!r || !handle) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, r->group_block));
+  std::memcpy(handle, &h, 64);
+  return VKGSB_OK;
+}
+
+int vkgsb_group_join(vkgsb_renderer* r, uint32_t rank, uint32_t world, const uint8_t* handles, const uint32_t* edges) {
+  if (!r || !handles || !edges) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (world > static_cast<uint32_t>(kMaxGroup)) return fail(VKGSB_ERR_INVALID, "at most 16 members");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  if (r->grouped) return fail(VKGSB_ERR_INVALID, "already a group member: vkgsb_group_leave first");
+  void* bases[kMaxGroup] = {nullptr};
+  bool ipc[kMaxGroup] = {false};
+  for (uint32_t m = 0; m < world; ++m) {
+    if (m == rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 64 * m, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&bases[m], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (uint32_t k = 0; k < m; ++k)
+        if (bases[k]) cudaIpcCloseMemHandle(bases[k]);
+      return fail(VKGSB_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
+    ipc[m] = true;
+  }
+  return group_setup(r, rank, world, bases, ipc, edges);
+}
+
+int vkgsb_group_join_local(vkgsb_renderer* const* members, uint32_t world, const uint32_t* edges) {
+  if (!members || !edges) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (world > static_cast<uint32_t>(kMaxGroup)) return fail(VKGSB_ERR_INVALID, "at most 16 members");
+  for (uint32_t m = 0; m < world; ++m) {
+    if (!members[m]) return fail(VKGSB_ERR_INVALID, "null member");
+    if (members[m]->grouped) return fail(VKGSB_ERR_INVALID, "already a group member");
+    if (members[m]->max_splats != members[0]->max_splats) return fail(VKGSB_ERR_INVALID, "members must share max_splats");
+  }
+  void* bases[kMaxGroup] = {nullptr};
+  bool ipc[kMaxGroup] = {false};
+  for (uint32_t m = 0; m < world; ++m) bases[m] = members[m]->group_block;
+  for (uint32_t m = 0; m < world; ++m) {
+    if (set_device(members[m])) return VKGSB_ERR_CUDA;
+    if (int e = group_setup(members[m], m, world, bases, ipc, edges)) return e;
+  }
+  return VKGSB_OK;
+}
+
+int vkgsb_group_leave(vkgsb_renderer* r) {
+  if (!r) return fail(VKGSB_ERR_INVALID, "renderer is null");
+  if (!r->grouped) return VKGSB_OK;
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  std::lock_guard<std::mutex> g(r->draw_mutex);
+  CU_TRY(cudaDeviceSynchronize());
+  for (int m = 0; m < kMaxGroup; ++m) {
+    if (r->group_peer_ipc[m] && r->group_peer_base[m]) cudaIpcCloseMemHandle(r->group_peer_base[m]);
+    r->group_peer_base[m] = nullptr;
+    r->group_peer_ipc[m] = false;
+  }
+  r->grouped = false;
+  r->band_y0 = r->band_y1 = 0;
+  invalidate_graph(r);
   return VKGSB_OK;
 }
 

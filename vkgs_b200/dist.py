@@ -1,7 +1,8 @@
 """Multi-GPU host logic.  The reference is single-GPU; the path shards two ways, both with the
 scene replicated per GPU and no collective on the data path except gathering finished pixels:
 
-  by view   cameras dealt to ranks in contiguous blocks; every rank runs the whole frame pipeline per view;
+  by view   cameras dealt to ranks round-robin (deal_views) or in contiguous blocks (shard_views); every rank runs the
+            whole frame pipeline per view;
             images are gathered to one rank (NCCL on GPUs, gloo in the CPU tests).
   by band   one view, rank g bins and blends only rows [edge[g], edge[g+1]) (VKGSB_OPT_BAND_Y0/Y1); the cull and the
             depth sort are replicated so every band sees the same global order; bands concatenate to the frame.
@@ -20,6 +21,12 @@ def shard_views(n_views: int, rank: int, world: int) -> range:
     base, extra = divmod(n_views, world)
     start = rank * base + min(rank, extra)
     return range(start, start + base + (1 if rank < extra else 0))
+
+
+def deal_views(n_views: int, rank: int, world: int) -> range:
+    """Views rank, rank + world, rank + 2 world, ...: neighbouring views of an orbit cost about the same, so dealing them
+    round-robin gives every rank the same mix (contiguous blocks leave the rank with the heaviest arc last)."""
+    return range(rank, n_views, world)
 
 
 def band_edges(height: int, world: int, align: int = 16) -> List[int]:

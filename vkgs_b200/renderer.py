@@ -172,6 +172,21 @@ class Renderer:
         L.check(L.lib().vkgsb_row_histogram(self._h, _ptr(rows), self.height))
         return rows
 
+    # ---- band group (one member per GPU)
+    def group_export(self) -> bytes:
+        h = (C.c_uint8 * 64)()
+        L.check(L.lib().vkgsb_group_export(self._h, h))
+        return bytes(h)
+
+    def group_join(self, rank: int, world: int, handles, edges):
+        """handles: `world` 64-byte handles in rank order (group_export of every member); edges: world + 1 rows."""
+        blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(bytes(h) for h in handles))
+        e = (C.c_uint32 * (world + 1))(*[int(x) for x in edges])
+        L.check(L.lib().vkgsb_group_join(self._h, int(rank), int(world), blob, e))
+
+    def group_leave(self):
+        L.check(L.lib().vkgsb_group_leave(self._h))
+
     # ---- parity taps
     def read_sorted(self):
         cnt = C.c_uint32()
@@ -218,6 +233,14 @@ def reference_overlay(show_axis: bool = True, show_grid: bool = True):
             col.append([g, g])
     model = np.diag([10.0, 10.0, 10.0, 1.0]).astype(np.float32).T.reshape(16)
     return (np.asarray(pos, np.float32).reshape(-1, 2, 3), np.asarray(col, np.float32).reshape(-1, 2, 4), model)
+
+
+def group_join_local(members, edges):
+    """Band group of renderers living in this process (member g draws rows [edges[g], edges[g + 1]))."""
+    n = len(members)
+    arr = (C.c_void_p * n)(*[m._h for m in members])
+    e = (C.c_uint32 * (n + 1))(*[int(x) for x in edges])
+    L.check(L.lib().vkgsb_group_join_local(arr, n, e))
 
 
 def shared_create(device: int, nbytes: int):
