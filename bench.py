@@ -243,22 +243,26 @@ class NcclGather:
     name = "images gathered to rank 0 (NCCL, batches of 4 frames, double-buffered)"
 
     def __init__(self, torch, dist, dev, world, rank, h, w, every=4, nbuf=2):
+        assert every == self.group
         self.dist, self.world, self.rank, self.every, self.nbuf = dist, world, rank, every, nbuf
         self.batches = [torch.empty((every, h, w, 4), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
         self.gathered = [[torch.empty_like(self.batches[0]) for _ in range(world)] if (world > 1 and rank == 0) else None
                          for _ in range(nbuf)]
         self.pending = [None] * nbuf
 
+    group = 4   # frames per vkgsb_draw_batch call = frames per gather
+
     def dst(self, i):
-        b, j = (i // self.every) % self.nbuf, i % self.every
-        if j == 0 and self.pending[b] is not None:   # the buffer's previous gather must have read it
+        """(device pointer of frame i, stride to frame i + 1) - i is a multiple of `group`"""
+        b = (i // self.every) % self.nbuf
+        if self.pending[b] is not None:   # the buffer's previous gather must have read it
             self.pending[b].wait()
             self.pending[b] = None
-        return self.batches[b][j].data_ptr()
+        return self.batches[b].data_ptr(), self.batches[b][0].numel()
 
-    def sent(self, i):
-        b, j = (i // self.every) % self.nbuf, i % self.every
-        if self.world > 1 and j == self.every - 1:
+    def sent(self, i, n):
+        b = (i // self.every) % self.nbuf
+        if self.world > 1:
             self.pending[b] = self.dist.gather(self.batches[b], self.gathered[b], dst=0, async_op=True)
 
     def drain(self):
@@ -276,8 +280,11 @@ class PeerWrite:
     (never reached inside a timed region shorter than `slots` steps)."""
     name = "every rank's blend kernel writes its pixels into rank 0's buffer over NVLink (CUDA IPC peer mapping, no NCCL on the data path)"
 
+    group = 4   # frames per vkgsb_draw_batch call
+
     def __init__(self, torch, dist, dev, world, rank, h, w, local, slots, images_per_slot=None):
         import vkgs_b200
+        slots = (slots + self.group - 1) // self.group * self.group
         self.dist, self.world, self.rank, self.slots = dist, world, rank, slots
         self.img = h * w * 4
         self.V = vkgs_b200
@@ -294,11 +301,12 @@ class PeerWrite:
         self.local = local
 
     def dst(self, i):
+        """(device pointer of frame i, stride to frame i + 1) - i is a multiple of `group`"""
         if self.world > 1 and i > 0 and i % self.slots == 0:
             self.dist.barrier()
-        return self.base + ((i % self.slots) * self.world + self.rank) * self.img
+        return self.base + ((i % self.slots) * self.world + self.rank) * self.img, self.world * self.img
 
-    def sent(self, i):
+    def sent(self, i, n):
         pass
 
     def drain(self):
@@ -416,28 +424,31 @@ def run_views(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
     else:
         deliver = NcclGather(torch, dist, dev, world, rank, H_, W_)
 
-    def frame_device(i):
-        r.set_camera(block=cams[i % len(cams)])
-        r.draw_device(dst_ptr=deliver.dst(i), stream=sptr)
-        deliver.sent(i)
+    G = deliver.group
+
+    def frames_device(k):
+        """k frames through the public batch call, G views at a time (the orbit usage: consecutive frames run side by side
+        on the device), every frame rendered straight into its destination"""
+        for i in range(0, k, G):
+            n = min(G, k - i)
+            ptr, stride = deliver.dst(i)
+            r.draw_batch([cams[(i + j) % len(cams)] for j in range(n)], dst_ptr=ptr, stride=stride, stream=sptr)
+            deliver.sent(i, n)
 
     def timed(mode):
         r.set_blend_mode(mode)
-        for i in range(W):
-            frame_device(i)
+        frames_device(W)
         deliver.drain()
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
-        for i in range(W):   # the GPU stays under load while the sampler comes up
-            frame_device(i)
+        frames_device(W)   # the GPU stays under load while the sampler comes up
         deliver.drain()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         sampler.mark_begin()
         e0.record(stream)
-        for i in range(K):
-            frame_device(i)
+        frames_device(K)
         deliver.drain()   # every image has arrived on rank 0 inside the timed region (peer writes: when the stream
         e1.record(stream)  # and the barrier below have completed)
         barrier()

@@ -213,6 +213,31 @@ VKGSB_API int vkgsb_group_join(vkgsb_renderer* r, uint32_t rank, uint32_t world,
 VKGSB_API int vkgsb_group_join_local(vkgsb_renderer* const* members, uint32_t world, const uint32_t* edges);
 VKGSB_API int vkgsb_group_leave(vkgsb_renderer* r);
 
+/* External memory and semaphores: the present path of a desktop viewer (the reference's interop pattern,
+ * src/vkgs/engine/interop/cuda_image.cu:77-132 and cuda_semaphore.cu:56-86, device extensions at
+ * src/vkgs/vulkan/context.cc:204-216,240-241).  The application creates its VkImage with exportable memory, takes the
+ * memory's file descriptor (vkGetMemoryFdKHR) and hands it over; the returned device pointer is a frame destination for
+ * vkgsb_draw(dst, dst_is_device = 1), so the blend kernel writes the frame straight into the image's memory (the
+ * reference measured its copy-based variant at 1 ms per 1600x900 frame, DETAILS.md:43).  On success an OPAQUE_FD belongs
+ * to CUDA and must not be closed by the caller.  VKGSB_EXTERNAL_CUDA_POSIX_FD is the same contract for an allocation
+ * exported by CUDA's own virtual-memory API (cuMemExportToShareableHandle) - another process's CUDA allocation, or the
+ * stand-in for the VkImage's memory where no Vulkan exists (tests); vkgsb_external_alloc creates such an allocation and
+ * returns its fd (the caller owns and closes the fd). */
+enum vkgsb_external_handle_type {
+  VKGSB_EXTERNAL_OPAQUE_FD = 0,     /* VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT (cudaExternalMemoryHandleTypeOpaqueFd) */
+  VKGSB_EXTERNAL_CUDA_POSIX_FD = 1  /* CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR */
+};
+typedef struct vkgsb_external vkgsb_external;
+VKGSB_API int vkgsb_external_import(int device, int fd, size_t bytes, int handle_type, vkgsb_external** out, void** d_ptr);
+VKGSB_API int vkgsb_external_alloc(int device, size_t bytes, vkgsb_external** out, int* fd, void** d_ptr);
+VKGSB_API int vkgsb_external_release(vkgsb_external* ext);
+/* A VkSemaphore exported as an opaque fd (vkGetSemaphoreFdKHR): signalled on `stream` behind a frame so that the queue
+ * presenting the image waits for it; waited on before a frame overwrites an image the other API still reads. */
+VKGSB_API int vkgsb_external_semaphore_import(int device, int fd, void** sem);
+VKGSB_API int vkgsb_external_semaphore_signal(void* sem, void* stream);
+VKGSB_API int vkgsb_external_semaphore_wait(void* sem, void* stream);
+VKGSB_API int vkgsb_external_semaphore_release(void* sem);
+
 /* Parity taps (test / debugging): state of the last drawn frame, copied to host.
  * read_sorted: keys/ids in sorted (far -> near) order = SplatStorage.key / .index after vrdx (engine.cc:1218-1219).
  * read_instances: 12 floats per visible splat in sorted order = SplatStorage.instance (projection.comp:177-179).

@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("VKGSB_LIB") or os.path.join(_HERE, "lib", "libvkgsb.s
 
 OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_CAPACITY, ERR_NO_SCENE, ERR_CANCELLED = range(7)
 BLEND_FP32, BLEND_UNORM8 = 0, 1
+EXTERNAL_OPAQUE_FD, EXTERNAL_CUDA_POSIX_FD = 0, 1
 FORMAT_RGBA8, FORMAT_BGRA8 = 0, 1
 OPT_STAGE_TIMING, OPT_BLEND_MODE, OPT_PIXEL_FORMAT, OPT_BAND_Y0, OPT_BAND_Y1, OPT_KEEP_INSTANCES, OPT_BAND_CULL, OPT_COUNT_FRAGMENTS, OPT_UNORM8_CUT_EXP, OPT_L2_PIN_MB = range(10)
 
@@ -68,6 +69,13 @@ SIGNATURES = {
     "vkgsb_group_join": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),
     "vkgsb_group_join_local": (C.c_int, [C.POINTER(_P), C.c_uint32, _P]),
     "vkgsb_group_leave": (C.c_int, [_P]),
+    "vkgsb_external_import": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
+    "vkgsb_external_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P), C.POINTER(C.c_int), C.POINTER(_P)]),
+    "vkgsb_external_release": (C.c_int, [_P]),
+    "vkgsb_external_semaphore_import": (C.c_int, [C.c_int, C.c_int, C.POINTER(_P)]),
+    "vkgsb_external_semaphore_signal": (C.c_int, [_P, _P]),
+    "vkgsb_external_semaphore_wait": (C.c_int, [_P, _P]),
+    "vkgsb_external_semaphore_release": (C.c_int, [_P]),
     "vkgsb_shared_create": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P), _P]),
     "vkgsb_shared_open": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "vkgsb_shared_close": (C.c_int, [C.c_int, _P]),

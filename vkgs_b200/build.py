@@ -35,6 +35,7 @@ SOURCES = {
     "bin.cu": os.environ.get("VKGSB_BIN_FLAGS", "").split(),
     "blend.cu": os.environ.get("VKGSB_BLEND_FLAGS", "").split(),
     "renderer.cu": [],
+    "interop.cu": [],
     "ply.cc": [],
     "camera.cc": [],
     "engine.cc": [],

@@ -57,22 +57,26 @@ struct vkgsb_renderer {
   SceneStorage scene{};
   std::atomic<uint32_t> scene_n{0};
 
-  // per-frame work buffers
-  uint32_t *keys = nullptr, *slots = nullptr, *keys_alt = nullptr, *slots_alt = nullptr, *vis_id = nullptr;
-  float* inst = nullptr;
-  float* rrec = nullptr;       // raster records by compacted slot (project.cu)
+  // Per-frame work buffers, TWO sets used by alternate frames (index p = the frame's parity): consecutive frames of a
+  // batch then run side by side on the sets' own streams (vkgsb_draw_batch), and a single frame's cull runs beside the
+  // previous frame's later stages (cull_stream).
+  uint32_t *keys[2] = {}, *slots[2] = {}, *keys_alt[2] = {}, *slots_alt[2] = {}, *vis_id = nullptr;
+  float* inst[2] = {};         // reference-format instance records: allocated when VKGSB_OPT_KEEP_INSTANCES is first set
+  float* rrec[2] = {};         // raster records by compacted slot (project.cu)
   // opaque line layer (vkgsb_set_lines): geometry, the per-pixel depth | colour words, the splats' ndc.z by slot
   uint32_t n_lines = 0;
-  float *line_pos = nullptr, *line_col = nullptr, *zndc = nullptr;
-  unsigned long long* layer = nullptr;
+  float *line_pos = nullptr, *line_col = nullptr, *zndc[2] = {};
+  unsigned long long* layer[2] = {};
   float line_model[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-  uint32_t* bin_rect = nullptr;  // coarse-bin box by compacted slot
-  uint32_t* bin_slots = nullptr;   // splat slots by coarse bin, nearest first (bin.cu); capacity max_pairs
-  BinScratch bin{};
-  uint32_t* lookback_depth = nullptr;
-  uint8_t* zero_region = nullptr;  // Control | coarse-bin ranges
+  uint32_t* bin_rect[2] = {};   // coarse-bin box by compacted slot
+  uint32_t* bin_slots[2] = {};  // splat slots by coarse bin, nearest first (bin.cu); capacity max_pairs
+  BinScratch bin[2]{};
+  uint32_t* lookback_depth[2] = {};
+  uint8_t* zero_region[2] = {};  // Control | coarse-bin ranges
   size_t zero_bytes = 0;
-  Control* ctrl = nullptr;
+  Control* ctrl[2] = {};
+  cudaStream_t slot_stream[2] = {nullptr, nullptr};  // the work-buffer sets' own streams (batches)
+  cudaStream_t slot_last_stream[2] = {nullptr, nullptr};  // the stream that last drew with set p
   // Two copies, used by alternate frames, of what a frame's cull needs and leaves: the parameter block and the cull index
   // (k_cull -> k_project, project.cu).  Frame f + 1's cull then runs on cull_stream while frame f is still in its
   // projection / sort / binning / blend on the frame's stream.
@@ -92,14 +96,13 @@ struct vkgsb_renderer {
   bool group_peer_ipc[kMaxGroup] = {false};
   uint64_t group_epoch = 0;  // frames drawn as a member; parity of a group frame = its epoch & 1 (the same on every member)
   int last_parity = 0;
-  uint2* ranges = nullptr;
+  uint2* ranges[2] = {};
   FrameParams* d_fp[2] = {nullptr, nullptr};
-  uint8_t* image = nullptr;
-  // draw_batch to host memory: frame i is copied out of stage[i & 1] on copy_stream while frame i + 1 renders
-  uint8_t* stage[2] = {nullptr, nullptr};
+  uint8_t* image[2] = {};
+  // draw_batch to host memory: a finished frame leaves image[p] over PCIe on copy_stream while the next frames render
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t frame_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
-  uint32_t* h_counts = nullptr;  // pinned: visible, pairs, overflow of the last frame
+  cudaEvent_t frame_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr}, batch_start = nullptr;
+  uint32_t* h_counts[2] = {};  // pinned: visible, pairs, overflow, ... of the set's last frame
 
   // load staging
   float* d_rows[2] = {nullptr, nullptr};
@@ -127,7 +130,6 @@ struct vkgsb_renderer {
   uint32_t graph_n[2] = {0, 0};
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t flight[4] = {nullptr, nullptr, nullptr, nullptr};  // end of frame f on the stream that drew it, at [f & 3]
-  cudaStream_t last_stream = nullptr;                            // the stream that drew the last frame
   bool ev_recorded = false;
   uint64_t frame_counter = 0;
   std::mutex draw_mutex;
@@ -158,6 +160,9 @@ cudaError_t drain_frames(vkgsb_renderer* r) {
   cudaError_t e = cudaStreamSynchronize(r->stream);
   if (e == cudaSuccess && r->cull_stream) e = cudaStreamSynchronize(r->cull_stream);
   if (e == cudaSuccess && r->frame_counter) e = cudaEventSynchronize(r->flight[r->frame_counter & 3]);
+  if (e == cudaSuccess && r->frame_counter > 1) e = cudaEventSynchronize(r->flight[(r->frame_counter - 1) & 3]);
+  for (cudaStream_t st : {r->slot_stream[0], r->slot_stream[1], r->copy_stream})
+    if (e == cudaSuccess && st) e = cudaStreamSynchronize(st);
   return e;
 }
 
@@ -387,10 +392,10 @@ int record_cull(vkgsb_renderer* r, int p, cudaStream_t s, bool clear = true) {
 // What a frame clears and draws before its splat stages, on `s`.
 int record_clears(vkgsb_renderer* r, int p, cudaStream_t s) {
   const uint32_t n = r->scene_n.load();
-  CU_TRY(cudaMemsetAsync(r->zero_region, 0, r->zero_bytes, s));
+  CU_TRY(cudaMemsetAsync(r->zero_region[p], 0, r->zero_bytes, s));
   // look-back words of the depth sort: only partitions of the <= n visible splats can be touched
-  CU_TRY(cudaMemsetAsync(r->lookback_depth, 0, sort_lookback_bytes(n), s));
-  if (r->n_lines) launch_lines(r->d_fp[p], r->n_lines, r->line_pos, r->line_col, r->width, r->height, r->layer, s);
+  CU_TRY(cudaMemsetAsync(r->lookback_depth[p], 0, sort_lookback_bytes(n), s));
+  if (r->n_lines) launch_lines(r->d_fp[p], r->n_lines, r->line_pos, r->line_col, r->width, r->height, r->layer[p], s);
   return VKGSB_OK;
 }
 
@@ -401,14 +406,14 @@ int record_stages(vkgsb_renderer* r, int p, cudaStream_t s, bool timed) {
   Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, n};
   FrameParams* d_fp = r->d_fp[p];
   // the depth sort runs an odd number of passes: its input goes to the ping-pong side, its result lands in keys / slots
-  launch_project(sc, d_fp, r->ctrl, r->cull[p], r->keys_alt, r->rrec, r->bin_rect, r->inst, r->n_lines ? r->zndc : nullptr, s);
+  launch_project(sc, d_fp, r->ctrl[p], r->cull[p], r->keys_alt[p], r->rrec[p], r->bin_rect[p], r->inst[p], r->n_lines ? r->zndc[p] : nullptr, s);
   if (r->grouped) launch_group_consumed(d_fp, r->group_flags, p, s);  // the others may write the next frame of this parity
   if (timed) CU_TRY(cudaEventRecord(r->ev[1], s));
   SortArgs depth{};
-  depth.d_count = &r->ctrl->visible_count;
+  depth.d_count = &r->ctrl[p]->visible_count;
   depth.max_n = n;
-  depth.keys = r->keys_alt; depth.vals = r->slots_alt; depth.keys_alt = r->keys; depth.vals_alt = r->slots;
-  depth.hist = r->ctrl->hist_depth; depth.tickets = r->ctrl->sort_ticket; depth.lookback = r->lookback_depth;
+  depth.keys = r->keys_alt[p]; depth.vals = r->slots_alt[p]; depth.keys_alt = r->keys[p]; depth.vals_alt = r->slots[p];
+  depth.hist = r->ctrl[p]->hist_depth; depth.tickets = r->ctrl[p]->sort_ticket; depth.lookback = r->lookback_depth[p];
   // k_project emits the depth key as the integer (1 - z) * 2^24 in [0, 2^24] (the float 1 - z is always a multiple of
   // 2^-24, so this is exact and ordered like the reference's float bits): 25 live bits = 3 passes of 8 + 8 + 9 bits
   // instead of the reference's 4 x 8 over the full word
@@ -419,13 +424,13 @@ int record_stages(vkgsb_renderer* r, int p, cudaStream_t s, bool timed) {
   depth.vals_identity = true;  // the value is the compacted slot: generated by the first pass
   launch_sort(depth, s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[2], s));
-  launch_bin(d_fp, r->h_fp.ncbins, r->ctrl, r->slots, r->bin_rect, n, r->max_pairs, r->bin, r->ranges, r->bin_slots, s);
+  launch_bin(d_fp, r->h_fp.ncbins, r->ctrl[p], r->slots[p], r->bin_rect[p], n, r->max_pairs, r->bin[p], r->ranges[p], r->bin_slots[p], s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[3], s));
-  launch_blend(d_fp, r->h_fp, r->ctrl, r->ranges, r->bin_slots, r->rrec, r->blend_mode,
-               r->pixel_format == VKGSB_FORMAT_BGRA8, r->count_fragments != 0, r->n_lines ? r->layer : nullptr, r->n_lines ? r->zndc : nullptr,
-               r->image, s);
+  launch_blend(d_fp, r->h_fp, r->ctrl[p], r->ranges[p], r->bin_slots[p], r->rrec[p], r->blend_mode,
+               r->pixel_format == VKGSB_FORMAT_BGRA8, r->count_fragments != 0, r->n_lines ? r->layer[p] : nullptr, r->n_lines ? r->zndc[p] : nullptr,
+               r->image[p], s);
   if (timed) CU_TRY(cudaEventRecord(r->ev[4], s));
-  CU_TRY(cudaMemcpyAsync(r->h_counts, r->ctrl, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(r->h_counts[p], r->ctrl[p], 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaGetLastError());
   return VKGSB_OK;
 }
@@ -438,8 +443,6 @@ int run_frame(vkgsb_renderer* r, cudaStream_t s, void* direct_dst = nullptr) {
   // nothing resident: an error, unless a load is under way or lines are set - the reference's window shows the clear
   // colour and the axis / grid while the first chunks are parsed
   if (n == 0 && r->n_lines == 0 && r->load_state.load() != 1) return fail(VKGSB_ERR_NO_SCENE, "no splats loaded");
-  // the work buffers are shared by all frames: a frame on another stream than the last one waits for it
-  if (r->frame_counter && s != r->last_stream) CU_TRY(cudaStreamWaitEvent(s, r->flight[r->frame_counter & 3], 0));
   fill_params(r);
   r->h_fp.dst_image = reinterpret_cast<unsigned long long>(direct_dst);
   const uint64_t f = r->frame_counter + 1;  // this frame
@@ -448,6 +451,8 @@ int run_frame(vkgsb_renderer* r, cudaStream_t s, void* direct_dst = nullptr) {
   const int p = static_cast<int>((r->grouped ? r->group_epoch : f) & 1);
   r->h_fp.epoch = static_cast<uint32_t>(r->group_epoch);
   r->last_parity = p;
+  // frame f - 2 used the same set of work buffers: a frame on another stream than that one waits for it
+  if (f > 2 && s != r->slot_last_stream[p]) CU_TRY(cudaStreamWaitEvent(s, r->flight[(f - 2) & 3], 0));
   if (r->stage_timing) {
     // eager, everything on the frame's stream, events between the stages
     k_set_params<<<1, 32, 0, s>>>(r->h_fp, r->d_fp[p]);
@@ -496,7 +501,7 @@ int run_frame(vkgsb_renderer* r, cudaStream_t s, void* direct_dst = nullptr) {
     r->ev_recorded = false;
   }
   r->frame_counter++;
-  r->last_stream = s;
+  r->slot_last_stream[p] = s;
   CU_TRY(cudaEventRecord(r->flight[r->frame_counter & 3], s));
   r->last_frame_has_instances = r->keep_instances != 0;
   return VKGSB_OK;
@@ -507,6 +512,9 @@ int run_frame(vkgsb_renderer* r, cudaStream_t s, void* direct_dst = nullptr) {
 extern "C" {
 
 const char* vkgsb_last_error(void) { return g_last_error.c_str(); }
+
+// for the other translation units of the library (interop.cu): the calling thread's error text
+__attribute__((visibility("hidden"))) void vkgsb_set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }
 
 int vkgsb_device_count(int* count) {
   if (!count) return fail(VKGSB_ERR_INVALID, "count is null");
@@ -567,24 +575,26 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   const size_t N = r->max_splats, P = r->max_pairs;
   ALLOC(r->scene.x, N * 4); ALLOC(r->scene.y, N * 4); ALLOC(r->scene.z, N * 4); ALLOC(r->scene.tr, N * 4);
   ALLOC(r->scene.payload, N * sizeof(SplatPayload));
-  ALLOC(r->keys, N * 4); ALLOC(r->slots, N * 4); ALLOC(r->keys_alt, N * 4); ALLOC(r->slots_alt, N * 4);
   ALLOC(r->vis_id, N * 4);
-  ALLOC(r->inst, N * 48);
-  ALLOC(r->rrec, N * 48);
-  ALLOC(r->bin_rect, N * 4);
-  ALLOC(r->bin_slots, bin_slots_capacity(P) * 4);
-  r->bin.tile_stride = bin_num_tiles(r->max_splats);
-  ALLOC(r->bin.tile_pairs, static_cast<size_t>(r->bin.tile_stride) * 4);
-  ALLOC(r->bin.tile_item, (static_cast<size_t>(r->bin.tile_stride) + 1) * 4);
-  ALLOC(r->bin.tile_bin, static_cast<size_t>(kMaxCoarseBins) * r->bin.tile_stride * 4);
-  ALLOC(r->bin.bin_total, kMaxCoarseBins * 4);
-  ALLOC(r->lookback_depth, sort_lookback_bytes(r->max_splats));
-  const CullIndexLayout cl = cull_index_layout(r->max_splats);
   const size_t ctrl_bytes = (sizeof(Control) + 255) & ~size_t(255);
   r->zero_bytes = ctrl_bytes + kMaxCoarseBins * sizeof(uint2);
-  ALLOC(r->zero_region, r->zero_bytes);
-  r->ctrl = reinterpret_cast<Control*>(r->zero_region);
-  r->ranges = reinterpret_cast<uint2*>(r->zero_region + ctrl_bytes);
+  for (int p = 0; p < 2; ++p) {
+    ALLOC(r->keys[p], N * 4); ALLOC(r->slots[p], N * 4); ALLOC(r->keys_alt[p], N * 4); ALLOC(r->slots_alt[p], N * 4);
+    ALLOC(r->rrec[p], N * 48);
+    ALLOC(r->bin_rect[p], N * 4);
+    ALLOC(r->bin_slots[p], bin_slots_capacity(P) * 4);
+    r->bin[p].tile_stride = bin_num_tiles(r->max_splats);
+    ALLOC(r->bin[p].tile_pairs, static_cast<size_t>(r->bin[p].tile_stride) * 4);
+    ALLOC(r->bin[p].tile_item, (static_cast<size_t>(r->bin[p].tile_stride) + 1) * 4);
+    ALLOC(r->bin[p].tile_bin, static_cast<size_t>(kMaxCoarseBins) * r->bin[p].tile_stride * 4);
+    ALLOC(r->bin[p].bin_total, kMaxCoarseBins * 4);
+    ALLOC(r->lookback_depth[p], sort_lookback_bytes(r->max_splats));
+    ALLOC(r->zero_region[p], r->zero_bytes);
+    r->ctrl[p] = reinterpret_cast<Control*>(r->zero_region[p]);
+    r->ranges[p] = reinterpret_cast<uint2*>(r->zero_region[p] + ctrl_bytes);
+    ALLOC(r->image[p], static_cast<size_t>(r->max_width) * r->max_height * 4);
+  }
+  const CullIndexLayout cl = cull_index_layout(r->max_splats);
   r->cull_tree_bytes = ((static_cast<size_t>(cl.na) + cl.nb + cl.nc + 63) & ~size_t(63)) * 4;
   {
     auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
@@ -611,13 +621,14 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
     r->cull[p].tile_cnt = reinterpret_cast<uint32_t*>(r->group_block + r->group_off_cnt[p]);
     ALLOC(r->d_fp[p], sizeof(FrameParams));
   }
-  ALLOC(r->image, static_cast<size_t>(r->max_width) * r->max_height * 4);
-  ALLOC(r->stage[0], static_cast<size_t>(r->max_width) * r->max_height * 4);
-  ALLOC(r->stage[1], static_cast<size_t>(r->max_width) * r->max_height * 4);
   ALLOC(r->d_offsets, 60 * 4);
 #undef ALLOC
-  if ((e = cudaMallocHost(reinterpret_cast<void**>(&r->h_counts), 64)) != cudaSuccess) return bail("cudaMallocHost", e);
-  std::memset(r->h_counts, 0, 64);
+  for (int p = 0; p < 2; ++p) {
+    if ((e = cudaMallocHost(reinterpret_cast<void**>(&r->h_counts[p]), 64)) != cudaSuccess) return bail("cudaMallocHost", e);
+    std::memset(r->h_counts[p], 0, 64);
+    if ((e = cudaStreamCreateWithFlags(&r->slot_stream[p], cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  }
+  if ((e = cudaEventCreateWithFlags(&r->batch_start, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
   for (auto& ev : r->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   for (auto& ev : r->chunk_done)
@@ -648,14 +659,24 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   if (r->load_stream) cudaStreamSynchronize(r->load_stream);
   for (cudaGraphExec_t g : {r->graph_cull[0], r->graph_cull[1], r->graph_main[0], r->graph_main[1]})
     if (g) cudaGraphExecDestroy(g);
-  void* dev[] = {r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, r->keys, r->slots, r->keys_alt, r->slots_alt,
-                 r->vis_id, r->inst, r->rrec, r->bin_rect, r->bin_slots, r->bin.tile_pairs, r->bin.tile_item, r->bin.tile_bin, r->bin.bin_total,
-                 r->lookback_depth, r->zero_region, r->group_block,
-                 r->cull_tree[0], r->cull_tree[1], r->d_fp[0], r->d_fp[1], r->image, r->stage[0], r->stage[1], r->d_offsets, r->d_rows[0],
-                 r->d_rows[1], r->line_pos, r->line_col, r->zndc, r->layer};
+  std::vector<void*> dev = {r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, r->vis_id, r->group_block,
+                            r->d_offsets, r->d_rows[0], r->d_rows[1], r->line_pos, r->line_col};
+  for (int p = 0; p < 2; ++p)
+    for (void* q : {static_cast<void*>(r->keys[p]), static_cast<void*>(r->slots[p]), static_cast<void*>(r->keys_alt[p]),
+                    static_cast<void*>(r->slots_alt[p]), static_cast<void*>(r->inst[p]), static_cast<void*>(r->rrec[p]),
+                    static_cast<void*>(r->bin_rect[p]), static_cast<void*>(r->bin_slots[p]), static_cast<void*>(r->bin[p].tile_pairs),
+                    static_cast<void*>(r->bin[p].tile_item), static_cast<void*>(r->bin[p].tile_bin),
+                    static_cast<void*>(r->bin[p].bin_total), static_cast<void*>(r->lookback_depth[p]),
+                    static_cast<void*>(r->zero_region[p]), static_cast<void*>(r->cull_tree[p]), static_cast<void*>(r->d_fp[p]),
+                    static_cast<void*>(r->image[p]), static_cast<void*>(r->zndc[p]), static_cast<void*>(r->layer[p])})
+      dev.push_back(q);
   for (void* p : dev)
     if (p) cudaFree(p);
-  if (r->h_counts) cudaFreeHost(r->h_counts);
+  for (int p = 0; p < 2; ++p) {
+    if (r->h_counts[p]) cudaFreeHost(r->h_counts[p]);
+    if (r->slot_stream[p]) cudaStreamDestroy(r->slot_stream[p]);
+  }
+  if (r->batch_start) cudaEventDestroy(r->batch_start);
   for (auto* p : r->h_rows)
     if (p) cudaFreeHost(p);
   for (auto& ev : r->ev)
@@ -690,7 +711,15 @@ int vkgsb_set_option(vkgsb_renderer* r, int option, int64_t value) {
       if (value != VKGSB_FORMAT_RGBA8 && value != VKGSB_FORMAT_BGRA8) return fail(VKGSB_ERR_INVALID, "bad pixel format");
       r->pixel_format = static_cast<int>(value);
       break;
-    case VKGSB_OPT_KEEP_INSTANCES: r->keep_instances = value != 0; break;
+    case VKGSB_OPT_KEEP_INSTANCES:
+      if (value != 0)
+        for (int p = 0; p < 2; ++p)
+          if (!r->inst[p]) {
+            if (set_device(r)) return VKGSB_ERR_CUDA;
+            CU_TRY(cudaMalloc(&r->inst[p], static_cast<size_t>(r->max_splats) * 48));
+          }
+      r->keep_instances = value != 0;
+      break;
     case VKGSB_OPT_BAND_Y0: r->band_y0 = static_cast<uint32_t>(value); break;
     case VKGSB_OPT_BAND_Y1: r->band_y1 = static_cast<uint32_t>(value); break;
     case VKGSB_OPT_BAND_CULL: r->band_cull = value != 0; break;
@@ -801,8 +830,10 @@ int vkgsb_set_lines(vkgsb_renderer* r, uint32_t n_lines, const float* positions,
   r->line_pos = r->line_col = nullptr;
   r->n_lines = 0;
   if (n_lines == 0) return VKGSB_OK;
-  if (!r->layer) CU_TRY(cudaMalloc(&r->layer, static_cast<size_t>(r->max_width) * r->max_height * sizeof(unsigned long long)));
-  if (!r->zndc) CU_TRY(cudaMalloc(&r->zndc, static_cast<size_t>(r->max_splats) * sizeof(float)));
+  for (int p = 0; p < 2; ++p) {
+    if (!r->layer[p]) CU_TRY(cudaMalloc(&r->layer[p], static_cast<size_t>(r->max_width) * r->max_height * sizeof(unsigned long long)));
+    if (!r->zndc[p]) CU_TRY(cudaMalloc(&r->zndc[p], static_cast<size_t>(r->max_splats) * sizeof(float)));
+  }
   CU_TRY(cudaMalloc(&r->line_pos, static_cast<size_t>(n_lines) * 6 * sizeof(float)));
   CU_TRY(cudaMalloc(&r->line_col, static_cast<size_t>(n_lines) * 8 * sizeof(float)));
   CU_TRY(cudaMemcpy(r->line_pos, positions, static_cast<size_t>(n_lines) * 6 * sizeof(float), cudaMemcpyHostToDevice));
@@ -822,12 +853,17 @@ int vkgsb_draw(vkgsb_renderer* r, void* dst, int dst_is_device, void* stream) {
   if (int e = run_frame(r, s, dst && dst_is_device ? dst : nullptr)) return e;
   const size_t bytes = static_cast<size_t>(r->width) * r->height * 4;
   if (dst && !dst_is_device) {
-    CU_TRY(cudaMemcpyAsync(dst, r->image, bytes, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(dst, r->image[r->last_parity], bytes, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
   }
   return VKGSB_OK;
 }
 
+// The frames of a batch need nothing from each other, so consecutive frames run SIDE BY SIDE: frame i on the stream of
+// work-buffer set i & 1, behind frame i - 2 only.  The memory-bound projection of one frame then shares the GPU with
+// the latency-bound sort and the issue-bound blend of the other (the reference keeps two frames in flight for the
+// same reason, engine.cc:1028-1035).  Everything the caller queued on `stream` before the call precedes the batch; the
+// stream continues when the whole batch has finished.
 int vkgsb_draw_batch(vkgsb_renderer* r, uint32_t n_views, const vkgsb_camera* cameras, void* dst, size_t dst_stride,
                      int dst_is_device, void* stream) {
   if (!r || !cameras) return fail(VKGSB_ERR_INVALID, "null argument");
@@ -836,40 +872,48 @@ int vkgsb_draw_batch(vkgsb_renderer* r, uint32_t n_views, const vkgsb_camera* ca
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : r->stream;
   const size_t bytes = static_cast<size_t>(r->width) * r->height * 4;
   if (dst && dst_stride < bytes) return fail(VKGSB_ERR_INVALID, "dst_stride smaller than one image");
-  if (dst && !dst_is_device) {
-    // Host destination: double-buffered.  The finished frame is parked in stage[i & 1] (a 2 us device copy) and leaves
-    // over PCIe on copy_stream while the next view renders; the render stream only waits for the copy that last read
-    // the stage it is about to overwrite.
-    bool used[2] = {false, false};
-    for (uint32_t i = 0; i < n_views; ++i) {
-      const int b = static_cast<int>(i & 1u);
-      r->cam = cameras[i];
-      r->have_cam = true;
-      if (int e = run_frame(r, s)) return e;
-      if (used[b]) CU_TRY(cudaStreamWaitEvent(s, r->copy_done[b], 0));
-      CU_TRY(cudaMemcpyAsync(r->stage[b], r->image, bytes, cudaMemcpyDeviceToDevice, s));
-      CU_TRY(cudaEventRecord(r->frame_done[b], s));
-      CU_TRY(cudaStreamWaitEvent(r->copy_stream, r->frame_done[b], 0));
-      CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + i * dst_stride, r->stage[b], bytes, cudaMemcpyDeviceToHost,
-                             r->copy_stream));
-      CU_TRY(cudaEventRecord(r->copy_done[b], r->copy_stream));
-      used[b] = true;
-    }
-    CU_TRY(cudaStreamSynchronize(r->copy_stream));  // returns when every image is in dst
-    CU_TRY(cudaStreamSynchronize(s));
-    return VKGSB_OK;
+  if (n_views == 0) return VKGSB_OK;
+  const bool host = dst && !dst_is_device;
+  // stage timing measures one frame at a time; a band group's members hand-shake frame by frame
+  const bool side_by_side = !r->stage_timing && !r->grouped && n_views > 1;
+  if (side_by_side) {
+    CU_TRY(cudaEventRecord(r->batch_start, s));
+    CU_TRY(cudaStreamWaitEvent(r->slot_stream[0], r->batch_start, 0));
+    CU_TRY(cudaStreamWaitEvent(r->slot_stream[1], r->batch_start, 0));
   }
+  bool copying[2] = {false, false};
   for (uint32_t i = 0; i < n_views; ++i) {
     r->cam = cameras[i];
     r->have_cam = true;
-    if (int e = run_frame(r, s, dst ? static_cast<uint8_t*>(dst) + i * dst_stride : nullptr)) return e;
+    const int p = static_cast<int>((r->grouped ? r->group_epoch + 1 : r->frame_counter + 1) & 1);  // the set run_frame will use
+    cudaStream_t fs = side_by_side ? r->slot_stream[p] : s;
+    // host destination: the frame leaves image[p] over PCIe on copy_stream while the next frames render; the set's next
+    // frame waits for that copy before it overwrites the image
+    if (host && copying[p]) CU_TRY(cudaStreamWaitEvent(fs, r->copy_done[p], 0));
+    if (int e = run_frame(r, fs, dst && dst_is_device ? static_cast<uint8_t*>(dst) + i * dst_stride : nullptr)) return e;
+    if (host) {
+      CU_TRY(cudaEventRecord(r->frame_done[p], fs));
+      CU_TRY(cudaStreamWaitEvent(r->copy_stream, r->frame_done[p], 0));
+      CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + i * dst_stride, r->image[p], bytes, cudaMemcpyDeviceToHost,
+                             r->copy_stream));
+      CU_TRY(cudaEventRecord(r->copy_done[p], r->copy_stream));
+      copying[p] = true;
+    }
+  }
+  if (side_by_side) {  // the caller's stream continues behind the last frame of either set
+    CU_TRY(cudaStreamWaitEvent(s, r->flight[r->frame_counter & 3], 0));
+    CU_TRY(cudaStreamWaitEvent(s, r->flight[(r->frame_counter - 1) & 3], 0));
+  }
+  if (host) {
+    CU_TRY(cudaStreamSynchronize(r->copy_stream));  // returns when every image is in dst
+    CU_TRY(cudaStreamSynchronize(s));
   }
   return VKGSB_OK;
 }
 
 int vkgsb_image_device_ptr(vkgsb_renderer* r, void** ptr) {
   if (!r || !ptr) return fail(VKGSB_ERR_INVALID, "null argument");
-  *ptr = r->image;
+  *ptr = r->image[r->last_parity];  // the last frame drawn without a destination
   return VKGSB_OK;
 }
 
@@ -906,11 +950,11 @@ int vkgsb_get_stats(vkgsb_renderer* r, vkgsb_stats* out) {
   std::memset(out, 0, sizeof(*out));
   out->total_point_count = r->total_points.load();
   out->loaded_point_count = r->loaded_points.load();
-  out->visible_point_count = r->h_counts[0];
-  out->pair_count = r->h_counts[1];
-  out->pair_overflow = r->h_counts[2];
-  out->blend_retries = r->h_counts[3];
-  out->fragment_count = static_cast<uint64_t>(r->h_counts[4]) | (static_cast<uint64_t>(r->h_counts[5]) << 32);
+  out->visible_point_count = r->h_counts[r->last_parity][0];
+  out->pair_count = r->h_counts[r->last_parity][1];
+  out->pair_overflow = r->h_counts[r->last_parity][2];
+  out->blend_retries = r->h_counts[r->last_parity][3];
+  out->fragment_count = static_cast<uint64_t>(r->h_counts[r->last_parity][4]) | (static_cast<uint64_t>(r->h_counts[r->last_parity][5]) << 32);
   out->frame_counter = r->frame_counter;
   if (r->ev_recorded) {
     CU_TRY(cudaEventElapsedTime(&out->ms_project, r->ev[0], r->ev[1]));
@@ -929,12 +973,12 @@ int vkgsb_read_sorted(vkgsb_renderer* r, uint32_t* keys, uint32_t* ids, uint32_t
   std::lock_guard<std::mutex> g(r->draw_mutex);
   CU_TRY(cudaDeviceSynchronize());
   uint32_t v = 0;
-  CU_TRY(cudaMemcpy(&v, &r->ctrl->visible_count, 4, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(&v, &r->ctrl[r->last_parity]->visible_count, 4, cudaMemcpyDeviceToHost));
   *count = v;
   if (v > capacity) return fail(VKGSB_ERR_CAPACITY, "capacity smaller than the visible count");
   if (v == 0) return VKGSB_OK;
   if (keys) {
-    CU_TRY(cudaMemcpy(keys, r->keys, v * 4ull, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(keys, r->keys[r->last_parity], v * 4ull, cudaMemcpyDeviceToHost));
     // the frame sorts the integer (1 - z) * 2^24; the tap returns the reference's key, floatBitsToUint(1 - z)
     // (rank.comp:40) - the conversion is exact both ways
     for (uint32_t i = 0; i < v; ++i) {
@@ -945,9 +989,9 @@ int vkgsb_read_sorted(vkgsb_renderer* r, uint32_t* keys, uint32_t* ids, uint32_t
   if (ids) {
     // slots_alt is free between frames: gather ids there; the ids by slot come from the frame's cull index
     launch_expand_ids(r->cull[r->last_parity], r->scene_n.load(), r->vis_id, r->stream);
-    launch_gather_sorted(r->ctrl, r->slots, r->vis_id, r->inst, v, r->slots_alt, nullptr, r->stream);
+    launch_gather_sorted(r->ctrl[r->last_parity], r->slots[r->last_parity], r->vis_id, r->inst[r->last_parity], v, r->slots_alt[r->last_parity], nullptr, r->stream);
     CU_TRY(cudaStreamSynchronize(r->stream));
-    CU_TRY(cudaMemcpy(ids, r->slots_alt, v * 4ull, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(ids, r->slots_alt[r->last_parity], v * 4ull, cudaMemcpyDeviceToHost));
   }
   return VKGSB_OK;
 }
@@ -960,7 +1004,7 @@ int vkgsb_row_histogram(vkgsb_renderer* r, uint32_t* rows, uint32_t capacity) {
   CU_TRY(cudaDeviceSynchronize());
   uint32_t* d_hist = nullptr;
   CU_TRY(cudaMalloc(&d_hist, r->height * sizeof(uint32_t)));
-  launch_row_histogram(r->ctrl, r->rrec, r->scene_n.load(), r->height, d_hist, r->stream);
+  launch_row_histogram(r->ctrl[r->last_parity], r->rrec[r->last_parity], r->scene_n.load(), r->height, d_hist, r->stream);
   cudaError_t e = cudaStreamSynchronize(r->stream);
   if (e == cudaSuccess) e = cudaMemcpy(rows, d_hist, r->height * sizeof(uint32_t), cudaMemcpyDeviceToHost);
   cudaFree(d_hist);
@@ -974,7 +1018,7 @@ int vkgsb_read_instances(vkgsb_renderer* r, float* inst, uint32_t capacity, uint
   std::lock_guard<std::mutex> g(r->draw_mutex);
   CU_TRY(cudaDeviceSynchronize());
   uint32_t v = 0;
-  CU_TRY(cudaMemcpy(&v, &r->ctrl->visible_count, 4, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(&v, &r->ctrl[r->last_parity]->visible_count, 4, cudaMemcpyDeviceToHost));
   *count = v;
   if (v > capacity) return fail(VKGSB_ERR_CAPACITY, "capacity smaller than the visible count");
   if (v == 0 || !inst) return VKGSB_OK;
@@ -982,7 +1026,7 @@ int vkgsb_read_instances(vkgsb_renderer* r, float* inst, uint32_t capacity, uint
     return fail(VKGSB_ERR_INVALID, "instance records were not kept: set VKGSB_OPT_KEEP_INSTANCES before drawing");
   float* tmp = nullptr;
   CU_TRY(cudaMalloc(&tmp, v * 48ull));
-  launch_gather_sorted(r->ctrl, r->slots, r->vis_id, r->inst, v, nullptr, tmp, r->stream);
+  launch_gather_sorted(r->ctrl[r->last_parity], r->slots[r->last_parity], r->vis_id, r->inst[r->last_parity], v, nullptr, tmp, r->stream);
   cudaError_t e = cudaStreamSynchronize(r->stream);
   if (e == cudaSuccess) e = cudaMemcpy(inst, tmp, v * 48ull, cudaMemcpyDeviceToHost);
   cudaFree(tmp);

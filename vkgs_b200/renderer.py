@@ -133,10 +133,12 @@ class Renderer:
         """One frame left on the device, asynchronous on `stream` (0 = the renderer's stream)."""
         L.check(L.lib().vkgsb_draw(self._h, C.c_void_p(dst_ptr) if dst_ptr else None, 1, C.c_void_p(stream)))
 
-    def draw_batch(self, cameras, out=None, dst_ptr: int = 0, stream: int = 0):
+    def draw_batch(self, cameras, out=None, dst_ptr: int = 0, stream: int = 0, stride: int = 0):
+        """n views, consecutive frames side by side on the device.  dst_ptr: device destination of view 0, view i goes to
+        dst_ptr + i * stride (default stride: one image); asynchronous on `stream`.  Otherwise -> host array [n, H, W, 4]."""
         n = len(cameras)
         arr = (L.CameraBlock * n)(*cameras)
-        stride = self.width * self.height * 4
+        stride = stride or self.width * self.height * 4
         if dst_ptr:
             L.check(L.lib().vkgsb_draw_batch(self._h, n, arr, C.c_void_p(dst_ptr), stride, 1, C.c_void_p(stream)))
             return None
@@ -233,6 +235,24 @@ def reference_overlay(show_axis: bool = True, show_grid: bool = True):
             col.append([g, g])
     model = np.diag([10.0, 10.0, 10.0, 1.0]).astype(np.float32).T.reshape(16)
     return (np.asarray(pos, np.float32).reshape(-1, 2, 3), np.asarray(col, np.float32).reshape(-1, 2, 4), model)
+
+
+def external_alloc(device: int, nbytes: int):
+    """Exportable device memory (the stand-in for a VkImage's memory): (handle, fd, device pointer); the caller closes fd."""
+    h, fd, p = C.c_void_p(), C.c_int(-1), C.c_void_p()
+    L.check(L.lib().vkgsb_external_alloc(int(device), int(nbytes), C.byref(h), C.byref(fd), C.byref(p)))
+    return h, fd.value, p.value
+
+
+def external_import(device: int, fd: int, nbytes: int, handle_type: int = L.EXTERNAL_OPAQUE_FD):
+    """Memory another API / process exported as a file descriptor -> (handle, device pointer usable as a frame destination)."""
+    h, p = C.c_void_p(), C.c_void_p()
+    L.check(L.lib().vkgsb_external_import(int(device), int(fd), int(nbytes), int(handle_type), C.byref(h), C.byref(p)))
+    return h, p.value
+
+
+def external_release(handle):
+    L.check(L.lib().vkgsb_external_release(handle))
 
 
 def group_join_local(members, edges):
