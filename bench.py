@@ -603,7 +603,7 @@ def run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
         edges = [0, H_]
     img_bytes = W_ * H_ * 4
     if world > 1 and args.gather == "peer":
-        deliver = PeerWrite(torch, dist, dev, world, rank, H_, W_, local, 2, images_per_slot=1)  # ONE frame per slot: every rank writes its rows of it
+        deliver = PeerWrite(torch, dist, dev, world, rank, H_, W_, local, 8, images_per_slot=1)  # ONE frame per slot: every rank writes its rows of it
     else:
         deliver = None
         frame = torch.zeros((H_, W_, 4), dtype=torch.uint8, device=dev)
@@ -621,11 +621,11 @@ def run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
     def step(i):
         r.set_camera(block=cams[i % len(cams)])
         if deliver is not None:
-            # every rank's blend kernel writes its band's rows straight into rank 0's frame (slot i & 1); the ranks meet
-            # before a slot is reused
-            if i >= 2:
+            # every rank's blend kernel writes its band's rows straight into rank 0's frame (slot i % 8); the ranks meet
+            # before the ring of slots wraps
+            if i > 0 and i % 8 == 0:
                 dist.barrier()
-            r.draw_device(dst_ptr=deliver.base + (i & 1) * img_bytes, stream=sptr)
+            r.draw_device(dst_ptr=deliver.base + (i % 8) * img_bytes, stream=sptr)
         else:
             r.draw_device(dst_ptr=frame.data_ptr(), stream=sptr)
             if world > 1:

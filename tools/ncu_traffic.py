@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Per-launch DRAM traffic of one kernel from an `ncu --set full` report -> a small JSON bench.py reads for
-roofline.traffic.  Usage: python tools/ncu_traffic.py report.ncu-rep kernel_regex out.json"""
+roofline.traffic.  Usage: python tools/ncu_traffic.py report.ncu-rep kernel_regex out.json [per_frame_regex]
+With per_frame_regex (e.g. k_project) the matched launches are SUMMED per frame: frames = launches matching that regex
+(a stage made of several kernels, like k_cull + k_project)."""
 import csv
 import io
 import json
@@ -21,6 +23,8 @@ for r in rows[2:]:
         launches.append(dict(read=float(r[ri]) * scale[units[ri]], write=float(r[wi]) * scale[units[wi]],
                              duration=float(r[ti]), duration_unit=units[ti]))
 n = len(launches)
+if len(sys.argv) > 4:
+    n = sum(1 for r in rows[2:] if len(r) == len(hdr) and re.search(sys.argv[4], r[ki])) or n
 res = {"kernel": kern, "launches": n, "report": rep.split("/")[-1],
        "dram_bytes_read_per_launch": sum(l["read"] for l in launches) / n,
        "dram_bytes_write_per_launch": sum(l["write"] for l in launches) / n,
