@@ -50,8 +50,8 @@ CONFIGS = {
                n_views=8, orbit=dict(r=6.0, phi_deg=70.0), theta0=30.0, max_pairs=400_000_000, scaling="strong",
                workload="C5 50,000,000 splats SH3 (70 % background), 3840x2160, camera r=6, one screen band per GPU"),
 }
-# kernels of one frame: set_params, cull, project, 3 depth onesweep passes, bin tiles / scan / place, blend
-KERNELS_PER_FRAME = 10
+# kernels of one frame: set_params, cull classify / mixed, project, 3 depth onesweep passes, bin tiles / scan / place, blend
+KERNELS_PER_FRAME = 11
 
 
 def view_camera(cfg, i):
@@ -557,7 +557,7 @@ def run_views(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
                      "p90": float(np.percentile(S["totals"], 90))},
         "sort_gkeys_per_s": V_mean / (stage["sort"] * 1e-3) / 1e9,
         "sort_hbm_frac": 68.0 * V_mean / (stage["sort"] * 1e-3) / 1e9 / hbm_peak,
-        "roofline": {"kernel": "k_cull + k_project (the projection stage)", "bound": "hbm", "achieved": proj_gbs,
+        "roofline": {"kernel": "k_cull_classify + k_cull_mixed + k_project (the projection stage)", "bound": "hbm", "achieved": proj_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": proj_gbs / hbm_peak, "traffic": traffic,
                      "traffic_source": traffic_src, "peak_kind": peak_kind, "algorithmic_bytes": alg_bytes,
                      "share_of_step": stage["project"] / stage["total"], "dominant_by_time": dominant},

@@ -118,9 +118,15 @@ enum vkgsb_option {
   VKGSB_OPT_UNORM8_CUT_EXP = 8, /* k in [1, 18], default 4: VKGSB_BLEND_UNORM8 starts its back-to-front walk where the
                                  transmittance of the splats in front is below 10^-k (deeper = fewer retries, longer
                                  walks); the result is certified either way */
-  VKGSB_OPT_L2_PIN_MB = 9     /* default 72: the centres (12 B/splat) of the first that-many MB of splats are kept in the
-                                 126 MB L2 across frames (evict_last), so the cull stream of a scene of up to ~6 M splats
-                                 is an L2 hit from the second frame on; 0 disables */
+  VKGSB_OPT_L2_PIN_MB = 9,    /* default 72: the centres (12 B/splat) of the first that-many MB of splats are kept in the
+                                 126 MB L2 across frames (evict_last), so the centre gathers of a scene of up to ~6 M
+                                 splats are L2 hits from the second frame on; 0 disables */
+  VKGSB_OPT_SPATIAL_ORDER = 10 /* default 1: a load stores the scene in Morton order of the splat centres (the reference
+                                 keeps the file's order, splat_load_thread.cc:138-159), so that the cull decides whole tiles
+                                 of 256 splats from their bounding box and the visible splats' payload is read in runs.
+                                 Pixels are the same; equal depth keys - which the reference orders by a race,
+                                 rank.comp:38 - are ordered by stored index.  vkgsb_read_order maps stored index -> index in
+                                 the file.  0: keep the file's order.  Applies to the next load. */
 };
 
 VKGSB_API const char* vkgsb_last_error(void);
@@ -242,11 +248,15 @@ VKGSB_API int vkgsb_external_semaphore_release(void* sem);
  * read_sorted: keys/ids in sorted (far -> near) order = SplatStorage.key / .index after vrdx (engine.cc:1218-1219).
  * read_instances: 12 floats per visible splat in sorted order = SplatStorage.instance (projection.comp:177-179).
  * read_scene: the activated scene in the reference layout (engine.cc:1639-1651): pos[n*3], cov[n*6],
- *             opacity[n], sh[n*48] (IEEE half bits). Any pointer may be NULL. */
+ *             opacity[n], sh[n*48] (IEEE half bits), in STORED order (the ids of read_sorted index it). Any pointer may
+ *             be NULL.
+ * read_order: order[i] = index in the loaded file / uploaded rows of stored splat i (VKGSB_OPT_SPATIAL_ORDER; the
+ *             identity when that option is off). */
 VKGSB_API int vkgsb_read_sorted(vkgsb_renderer* r, uint32_t* keys, uint32_t* ids, uint32_t capacity, uint32_t* count);
 VKGSB_API int vkgsb_read_instances(vkgsb_renderer* r, float* inst, uint32_t capacity, uint32_t* count);
 VKGSB_API int vkgsb_read_scene(vkgsb_renderer* r, float* pos, float* cov, float* opacity, uint16_t* sh,
                                uint32_t capacity, uint32_t* count);
+VKGSB_API int vkgsb_read_order(vkgsb_renderer* r, uint32_t* order, uint32_t capacity, uint32_t* count);
 
 /* Stage-level plug-in for the sort alone, the vrdx* surface of third_party/vulkan_radix_sort
  * (include/vk_radix_sort.h:19-76): ascending, stable, in place, element count read ON THE DEVICE from d_count

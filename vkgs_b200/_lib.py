@@ -12,7 +12,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_CAPACITY, ERR_NO_SCENE, ERR_CANCELLED = r
 BLEND_FP32, BLEND_UNORM8 = 0, 1
 EXTERNAL_OPAQUE_FD, EXTERNAL_CUDA_POSIX_FD = 0, 1
 FORMAT_RGBA8, FORMAT_BGRA8 = 0, 1
-OPT_STAGE_TIMING, OPT_BLEND_MODE, OPT_PIXEL_FORMAT, OPT_BAND_Y0, OPT_BAND_Y1, OPT_KEEP_INSTANCES, OPT_BAND_CULL, OPT_COUNT_FRAGMENTS, OPT_UNORM8_CUT_EXP, OPT_L2_PIN_MB = range(10)
+OPT_STAGE_TIMING, OPT_BLEND_MODE, OPT_PIXEL_FORMAT, OPT_BAND_Y0, OPT_BAND_Y1, OPT_KEEP_INSTANCES, OPT_BAND_CULL, OPT_COUNT_FRAGMENTS, OPT_UNORM8_CUT_EXP, OPT_L2_PIN_MB, OPT_SPATIAL_ORDER = range(11)
 
 
 class Config(C.Structure):
@@ -63,6 +63,7 @@ SIGNATURES = {
     "vkgsb_read_sorted": (C.c_int, [_P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "vkgsb_read_instances": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "vkgsb_read_scene": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "vkgsb_read_order": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "vkgsb_sort_storage_bytes": (C.c_int, [C.c_uint32, C.POINTER(C.c_size_t)]),
     "vkgsb_sort_key_value_indirect": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "vkgsb_group_export": (C.c_int, [_P, _P]),

@@ -31,6 +31,7 @@ SOURCES = {
     "project.cu": ["-fmad=false"] + os.environ.get("VKGSB_PROJECT_FLAGS", "").split(),
     "load.cu": ["-fmad=false"],
     "lines.cu": ["-fmad=false"],
+    "spatial.cu": [],
     "sort.cu": os.environ.get("VKGSB_SORT_FLAGS", "").split(),
     "bin.cu": os.environ.get("VKGSB_BIN_FLAGS", "").split(),
     "blend.cu": os.environ.get("VKGSB_BLEND_FLAGS", "").split(),

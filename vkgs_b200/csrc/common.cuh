@@ -42,6 +42,9 @@ struct Scene {
   const float* tr;  // largest eigenvalue of the 3-D covariance (max scale^2): only the band cull reads it
   const SplatPayload* payload;
   uint32_t n;
+  // bounding boxes of the tiles of 256 consecutive splats (spatial.cu): box[2t] = (min x, min y, min z, max lambda_max
+  // of the tile), box[2t + 1] = (max x, max y, max z, 0); min x = NaN when the tile holds a non-finite centre
+  const float4* box;
 };
 
 // ---- per-frame parameter block (device copy of uniforms.h:10-15 + derived values) ----------------------------

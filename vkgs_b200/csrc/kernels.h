@@ -25,6 +25,21 @@ void launch_activate(const float* d_rows, const uint32_t* d_offsets, uint32_t fi
 void launch_export_scene(const SceneStorage& src, uint32_t n, float* d_pos, float* d_cov, float* d_opacity,
                          uint16_t* d_sh, cudaStream_t stream);
 
+// ---- spatial.cu: load-time spatial (Morton) order of the scene + tile bounding boxes ------------------------------
+struct SpatialStats {                 // of the finite centres
+  uint32_t min_ord[3], max_ord[3];    // bounding box (order-preserving integer images of the floats)
+  unsigned long long sum[3], sumsq[3], finite;  // moments of the box fractions in 16-bit fixed point; their count
+};
+// d_keys[i] = 30-bit Morton key of splat i's centre, d_vals[i] = i (sorted by key -> the stored order)
+void launch_spatial_keys(const SceneStorage& sc, uint32_t n, SpatialStats* d_stats, uint32_t* d_keys, uint32_t* d_vals,
+                         cudaStream_t stream);
+// every array of the scene: new[i] = old[d_order[i]], through d_tmp (n * 128 bytes); nonzero on a launch error
+int spatial_permute(const SceneStorage& sc, const uint32_t* d_order, uint32_t n, void* d_tmp, cudaStream_t stream);
+void launch_iota(uint32_t* d_v, uint32_t first, uint32_t count, cudaStream_t stream);
+// boxes of tiles [first_tile, first_tile + n_tiles) of a scene of n splats
+void launch_tile_boxes(const SceneStorage& sc, uint32_t n, uint32_t first_tile, uint32_t n_tiles, float4* d_box,
+                       cudaStream_t stream);
+
 // ---- project.cu ------------------------------------------------------------------------------------------------
 int sm_count();                          // SMs of the current device (cached)
 uint32_t project_num_tiles(uint32_t n);  // tiles of 256 splats
@@ -35,6 +50,8 @@ struct CullIndex {
   uint32_t* lvl_a;     // [na] sums over 32 tiles      } zero on entry
   uint32_t* lvl_b;     // [nb] sums over 32 A entries  }
   uint32_t* lvl_c;     // [nc] sums over 32 B entries  }
+  uint32_t* mixed_cnt;   // [1] zero on entry: tiles the frame tests per splat (cut by the frustum / near the band) ...
+  uint32_t* mixed_tile;  // [tiles] ... and which
 };
 struct CullIndexLayout {
   uint32_t tiles, na, nb, nc;
@@ -63,10 +80,10 @@ void launch_group_tree(const FrameParams* d_fp, const GroupParams& gp, int parit
 // after k_project: this member's cull index of the frame may be overwritten
 void launch_group_consumed(const FrameParams* d_fp, GroupFlags* own, int parity, cudaStream_t stream);
 
-// k_cull: the scene's centres -> cull index `ix` (its upper levels zero on entry).  Reads only the parameter block and
-// the scene, so a frame's cull may run while the previous frame is still in its later stages.
-// band_mode: FrameParams::flags has kFlagBandCull (the launch also stages the splats' lambda_max)
-void launch_cull(const Scene& scene, const FrameParams* d_fp, const CullIndex& ix, bool band_mode, cudaStream_t stream);
+// The cull: k_cull_classify decides every tile it can from its bounding box, k_cull_mixed tests the splats of the
+// others -> cull index `ix` (its upper levels and mixed_cnt zero on entry).  Reads only the parameter block and the
+// scene, so a frame's cull may run while the previous frame is still in its later stages.
+void launch_cull(const Scene& scene, const FrameParams* d_fp, const CullIndex& ix, cudaStream_t stream);
 // k_project.  d_rrec: 3 x float4 raster record per visible slot; d_inst: 12-float instance record (written only when
 // FrameParams.flags has kFlagKeepInstances).  Also accumulates the depth-key digit histograms in Control and writes
 // Control::visible_count.

@@ -56,6 +56,12 @@ struct vkgsb_renderer {
   // resident scene
   SceneStorage scene{};
   std::atomic<uint32_t> scene_n{0};
+  // spatial order (spatial.cu): the scene is stored in Morton order of the centres; order[i] = index in the file of stored
+  // splat i; boxes = the bounding box of every tile of 256 stored splats (what the cull classifies tiles from)
+  float4* boxes = nullptr;
+  uint32_t* order = nullptr;
+  SpatialStats* d_stats = nullptr;
+  int spatial_order = 1;  // VKGSB_OPT_SPATIAL_ORDER
 
   // Per-frame work buffers, TWO sets used by alternate frames (index p = the frame's parity): consecutive frames of a
   // batch then run side by side on the sets' own streams (vkgsb_draw_batch), and a single frame's cull runs beside the
@@ -81,7 +87,8 @@ struct vkgsb_renderer {
   // (k_cull -> k_project, project.cu).  Frame f + 1's cull then runs on cull_stream while frame f is still in its
   // projection / sort / binning / blend on the frame's stream.
   CullIndex cull[2]{};
-  uint32_t* cull_tree[2] = {nullptr, nullptr};  // the upper levels of cull[p]'s count tree: zeroed before every cull
+  uint32_t* cull_tree[2] = {nullptr, nullptr};  // the upper levels of cull[p]'s count tree + its mixed-tile count: zeroed before every cull
+  uint32_t* mixed_tile[2] = {nullptr, nullptr};  // cull[p]'s list of tiles tested per splat
   size_t cull_tree_bytes = 0;
   cudaStream_t cull_stream = nullptr;
   cudaEvent_t cull_done[2] = {nullptr, nullptr};
@@ -184,6 +191,36 @@ int ensure_row_staging(vkgsb_renderer* r, uint32_t stride_bytes) {
   return VKGSB_OK;
 }
 
+// The resident scene (n splats, file order, no frame in flight) -> Morton order of the centres (spatial.cu) + tile boxes.
+// Uses work-buffer set 0 for the sort and a temporary of n * 128 bytes; when that cannot be allocated the scene simply
+// stays in file order (slower frames, same pixels).
+int spatial_reorder(vkgsb_renderer* r, uint32_t n) {
+  cudaStream_t ls = r->load_stream;
+  void* tmp = nullptr;
+  if (cudaMalloc(&tmp, static_cast<size_t>(n) * sizeof(SplatPayload)) != cudaSuccess) {
+    cudaGetLastError();
+    return VKGSB_OK;
+  }
+  CU_TRY(cudaMemsetAsync(r->zero_region[0], 0, r->zero_bytes, ls));
+  launch_spatial_keys(r->scene, n, r->d_stats, r->keys[0], r->slots[0], ls);
+  CU_TRY(cudaMemcpyAsync(&r->ctrl[0]->visible_count, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, ls));
+  SortArgs a{};
+  a.d_count = &r->ctrl[0]->visible_count;
+  a.max_n = n;
+  a.keys = r->keys[0]; a.vals = r->slots[0]; a.keys_alt = r->keys_alt[0]; a.vals_alt = r->slots_alt[0];
+  a.hist = r->ctrl[0]->hist_depth; a.tickets = r->ctrl[0]->sort_ticket; a.lookback = r->lookback_depth[0];
+  a.begin_bit = 0; a.npass = 4;  // 4 x 8 bits (the keys have 30): an even pass count, the result lands in keys / vals
+  launch_sort(a, ls);
+  CU_TRY(cudaMemcpyAsync(r->order, r->slots[0], static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, ls));
+  const int pe = spatial_permute(r->scene, r->order, n, tmp, ls);
+  launch_tile_boxes(r->scene, n, 0, (n + 255u) / 256u, r->boxes, ls);
+  cudaError_t e = cudaStreamSynchronize(ls);
+  cudaFree(tmp);
+  if (pe || e != cudaSuccess) return fail(VKGSB_ERR_CUDA, std::string("spatial reorder: ") + cudaGetErrorString(e));
+  CU_TRY(cudaGetLastError());
+  return VKGSB_OK;
+}
+
 // Streamed ingest shared by upload_splats (memory source) and load_ply (file source): 65 536-vertex chunks through
 // two pinned buffers, H2D and activation of chunk k overlapping the host fill of chunk k+1.
 // fill(dst, first_vertex, count) returns false on a short read.
@@ -227,6 +264,10 @@ int ingest(vkgsb_renderer* r, uint64_t n64, uint32_t stride_bytes, const uint32_
     CU_TRY(cudaMemcpyAsync(r->d_rows[buf], r->h_rows[buf], static_cast<size_t>(count) * stride_bytes,
                            cudaMemcpyHostToDevice, r->load_stream));
     launch_activate(r->d_rows[buf], r->d_offsets, static_cast<uint32_t>(start), count, r->scene, r->load_stream);
+    // in file order until the whole scene is resident: boxes of the chunk's tiles (a chunk is a whole number of tiles)
+    launch_tile_boxes(r->scene, static_cast<uint32_t>(start + count), static_cast<uint32_t>(start / 256u), (count + 255u) / 256u,
+                      r->boxes, r->load_stream);
+    launch_iota(r->order, static_cast<uint32_t>(start), count, r->load_stream);
     CU_TRY(cudaEventRecord(r->chunk_done[buf], r->load_stream));
     r->loaded_points.store(static_cast<uint32_t>(start + count));
   }
@@ -234,6 +275,11 @@ int ingest(vkgsb_renderer* r, uint64_t n64, uint32_t stride_bytes, const uint32_
   CU_TRY(cudaGetLastError());
   {
     std::lock_guard<std::mutex> g(r->draw_mutex);
+    if (r->spatial_order && n > 1) {
+      // frames drawn during the load read the file-ordered prefix: drain them, then store the scene in spatial order
+      CU_TRY(drain_frames(r));
+      if (int e = spatial_reorder(r, n)) return e;
+    }
     r->scene_n.store(n);
     invalidate_graph(r);
   }
@@ -371,7 +417,7 @@ void fill_params(vkgsb_renderer* r) {
 // The cull of a frame (parity p) on `s`: count tree cleared, k_cull.
 int record_cull(vkgsb_renderer* r, int p, cudaStream_t s, bool clear = true) {
   const uint32_t n = r->scene_n.load();
-  Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, n};
+  Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, n, r->boxes};
   if (clear) CU_TRY(cudaMemsetAsync(r->cull_tree[p], 0, r->cull_tree_bytes, s));
   if (r->grouped) {
     // this member's share of the scene against every band, written into the bands' members; then wait for the others'
@@ -383,7 +429,7 @@ int record_cull(vkgsb_renderer* r, int p, cudaStream_t s, bool clear = true) {
     launch_cull_group(sc, r->d_fp[p], gp, p, s);
     launch_group_tree(r->d_fp[p], gp, p, n, s);
   } else {
-    launch_cull(sc, r->d_fp[p], r->cull[p], (r->h_fp.flags & kFlagBandCull) != 0u, s);
+    launch_cull(sc, r->d_fp[p], r->cull[p], s);
   }
   CU_TRY(cudaGetLastError());
   return VKGSB_OK;
@@ -403,7 +449,7 @@ int record_clears(vkgsb_renderer* r, int p, cudaStream_t s) {
 // cull and ev[5] behind it).
 int record_stages(vkgsb_renderer* r, int p, cudaStream_t s, bool timed) {
   const uint32_t n = r->scene_n.load();
-  Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, n};
+  Scene sc{r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, n, r->boxes};
   FrameParams* d_fp = r->d_fp[p];
   // the depth sort runs an odd number of passes: its input goes to the ping-pong side, its result lands in keys / slots
   launch_project(sc, d_fp, r->ctrl[p], r->cull[p], r->keys_alt[p], r->rrec[p], r->bin_rect[p], r->inst[p], r->n_lines ? r->zndc[p] : nullptr, s);
@@ -576,6 +622,9 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
   ALLOC(r->scene.x, N * 4); ALLOC(r->scene.y, N * 4); ALLOC(r->scene.z, N * 4); ALLOC(r->scene.tr, N * 4);
   ALLOC(r->scene.payload, N * sizeof(SplatPayload));
   ALLOC(r->vis_id, N * 4);
+  ALLOC(r->order, N * 4);
+  ALLOC(r->boxes, static_cast<size_t>(project_num_tiles(r->max_splats)) * 2 * sizeof(float4));
+  ALLOC(r->d_stats, sizeof(SpatialStats));
   const size_t ctrl_bytes = (sizeof(Control) + 255) & ~size_t(255);
   r->zero_bytes = ctrl_bytes + kMaxCoarseBins * sizeof(uint2);
   for (int p = 0; p < 2; ++p) {
@@ -595,7 +644,7 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
     ALLOC(r->image[p], static_cast<size_t>(r->max_width) * r->max_height * 4);
   }
   const CullIndexLayout cl = cull_index_layout(r->max_splats);
-  r->cull_tree_bytes = ((static_cast<size_t>(cl.na) + cl.nb + cl.nc + 63) & ~size_t(63)) * 4;
+  r->cull_tree_bytes = ((static_cast<size_t>(cl.na) + cl.nb + cl.nc + 1 + 63) & ~size_t(63)) * 4;  // + the mixed-tile count
   {
     auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
     size_t o = 0;
@@ -617,6 +666,9 @@ int vkgsb_create_ex(const vkgsb_config* cfg, vkgsb_renderer** out) {
     r->cull[p].lvl_a = r->cull_tree[p];
     r->cull[p].lvl_b = r->cull[p].lvl_a + cl.na;
     r->cull[p].lvl_c = r->cull[p].lvl_b + cl.nb;
+    r->cull[p].mixed_cnt = r->cull[p].lvl_c + cl.nc;
+    ALLOC(r->mixed_tile[p], static_cast<size_t>(cl.tiles) * 4);
+    r->cull[p].mixed_tile = r->mixed_tile[p];
     r->cull[p].mask = reinterpret_cast<uint32_t*>(r->group_block + r->group_off_mask[p]);
     r->cull[p].tile_cnt = reinterpret_cast<uint32_t*>(r->group_block + r->group_off_cnt[p]);
     ALLOC(r->d_fp[p], sizeof(FrameParams));
@@ -660,6 +712,7 @@ void vkgsb_destroy(vkgsb_renderer* r) {
   for (cudaGraphExec_t g : {r->graph_cull[0], r->graph_cull[1], r->graph_main[0], r->graph_main[1]})
     if (g) cudaGraphExecDestroy(g);
   std::vector<void*> dev = {r->scene.x, r->scene.y, r->scene.z, r->scene.tr, r->scene.payload, r->vis_id, r->group_block,
+                            r->order, r->boxes, r->d_stats, r->mixed_tile[0], r->mixed_tile[1],
                             r->d_offsets, r->d_rows[0], r->d_rows[1], r->line_pos, r->line_col};
   for (int p = 0; p < 2; ++p)
     for (void* q : {static_cast<void*>(r->keys[p]), static_cast<void*>(r->slots[p]), static_cast<void*>(r->keys_alt[p]),
@@ -728,6 +781,7 @@ int vkgsb_set_option(vkgsb_renderer* r, int option, int64_t value) {
       if (value < 0 || value > 4096) return fail(VKGSB_ERR_INVALID, "L2 pin size out of range");
       r->l2_pin_mb = static_cast<int>(value);
       break;
+    case VKGSB_OPT_SPATIAL_ORDER: r->spatial_order = value != 0; break;
     case VKGSB_OPT_UNORM8_CUT_EXP:
       if (value < 1 || value > 18) return fail(VKGSB_ERR_INVALID, "unorm8 cut exponent must be in [1, 18]");
       r->unorm8_cut = std::pow(10.f, -static_cast<float>(value));
@@ -1059,6 +1113,17 @@ int vkgsb_read_scene(vkgsb_renderer* r, float* pos, float* cov, float* opacity, 
   if (sh && e == cudaSuccess) e = cudaMemcpy(sh, ds, n * 96ull, cudaMemcpyDeviceToHost);
   cudaFree(dp); cudaFree(dc); cudaFree(dop); cudaFree(ds);
   CU_TRY(e);
+  return VKGSB_OK;
+}
+
+int vkgsb_read_order(vkgsb_renderer* r, uint32_t* order, uint32_t capacity, uint32_t* count) {
+  if (!r || !count) return fail(VKGSB_ERR_INVALID, "null argument");
+  if (set_device(r)) return VKGSB_ERR_CUDA;
+  const uint32_t n = r->scene_n.load();
+  *count = n;
+  if (!order) return VKGSB_OK;
+  if (n > capacity) return fail(VKGSB_ERR_CAPACITY, "capacity smaller than the scene");
+  if (n) CU_TRY(cudaMemcpy(order, r->order, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost));
   return VKGSB_OK;
 }
 

@@ -204,7 +204,17 @@ class Renderer:
         L.check(L.lib().vkgsb_read_instances(self._h, _ptr(inst), cap, C.byref(cnt)))
         return inst[:cnt.value].copy()
 
+    def read_order(self) -> np.ndarray:
+        """order[i] = index in the loaded file / uploaded rows of stored splat i (the scene is stored in Morton order of
+        the centres unless OPT_SPATIAL_ORDER is 0)."""
+        cnt = C.c_uint32()
+        L.check(L.lib().vkgsb_read_order(self._h, None, 0, C.byref(cnt)))
+        order = np.empty(max(cnt.value, 1), np.uint32)
+        L.check(L.lib().vkgsb_read_order(self._h, _ptr(order), cnt.value, C.byref(cnt)))
+        return order[:cnt.value].copy()
+
     def read_scene(self):
+        """The activated scene in the reference layout, in STORED order (what read_sorted's ids index)."""
         cnt = C.c_uint32()
         L.check(L.lib().vkgsb_read_scene(self._h, None, None, None, None, 0xFFFFFFFF, C.byref(cnt)))
         n = cnt.value
