@@ -363,6 +363,8 @@ def main():
     W_, H_ = cfg["width"], cfg["height"]
     rows = make_scene(cfg)
     r = vkgs_b200.Renderer(device=local, max_splats=cfg["n_splats"], max_width=W_, max_height=H_, max_pairs=cfg["max_pairs"])
+    if os.environ.get("VKGSB_SPATIAL_ORDER"):      # experiments: 0 keeps the file's order (no spatial order of the stored scene)
+        r.set_option(L.OPT_SPATIAL_ORDER, int(os.environ["VKGSB_SPATIAL_ORDER"]))
     r.upload_splats(rows)
     if not (world == 1 and not args.no_cpu_baseline and args.config == "c2"):
         del rows
