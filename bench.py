@@ -331,7 +331,7 @@ def main():
     ap.add_argument("--blend", default="fp32", choices=["fp32", "unorm8"], help="blend mode of the headline `value`")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="how finished images reach rank 0 (N > 1)")
     ap.add_argument("--n-splats", type=int, default=0, help="override the scene size (experiments)")
-    ap.add_argument("--band-cull", default="shared", choices=["shared", "replicated"],
+    ap.add_argument("--band-cull", default="replicated", choices=["shared", "replicated"],
                     help="c5: the cull shared out over the ranks (vkgsb_group_*: each rank tests 1/N of the splats against "
                          "every band and writes the bands' bits into their GPUs) or repeated over the whole scene by every rank")
     args = ap.parse_args()
@@ -611,6 +611,23 @@ def run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
         frame = torch.zeros((H_, W_, 4), dtype=torch.uint8, device=dev)
         gathered = [torch.empty_like(frame) for _ in range(world)] if (world > 1 and rank == 0) else None
     grouped = world > 1 and args.band_cull == "shared"
+    if world > 1 and not grouped:
+        # feedback: the centre histogram does not know what a band costs apart from its splats (the cull over its
+        # frustum, the blend's per-pixel work), so the edges are re-cut twice from the bands' measured stage times
+        for _ in range(2):
+            r.set_band(edges[rank], edges[rank + 1])
+            r.set_option(L.OPT_STAGE_TIMING, 1)
+            t_band = 0.0
+            for i in range(2 + 6):
+                r.set_camera(block=cams[i % len(cams)])
+                r.draw_device()
+                if i >= 2:
+                    t_band += r.stats()["ms_total"] / 6
+            r.set_option(L.OPT_STAGE_TIMING, 0)
+            r.sync()
+            t_all = [None] * world
+            dist.all_gather_object(t_all, float(t_band))
+            edges = vdist.rebalance_band_edges(edges, t_all)
     if grouped:
         handles = [None] * world
         dist.all_gather_object(handles, r.group_export())
@@ -680,7 +697,7 @@ def run_bands(args, cfg, r, torch, dist, vdist, L, dev, world, rank, local, stre
         "data": "synthetic",
         "config": {"workload": cfg["workload"], "blend": args.blend, "band_edges": edges,
                    "parallelism": (f"{world} screen bands on {world} GPU(s), scene replicated, band edges balanced on the row "
-                                   "histogram; cull " + ("shared out over the ranks, each band's visibility bits written into its GPU "
+                                   "histogram" + ("" if grouped else " and re-cut twice from the bands' measured times") + "; cull " + ("shared out over the ranks, each band's visibility bits written into its GPU "
                                                          "over NVLink (no collective); " if grouped else "repeated by every rank; ") + (PeerWrite.name if deliver is not None else "bands gathered to rank 0 (NCCL)"))
                    if world > 1 else "single GPU, whole frame",
                    "l2": f"inputs larger than L2: {144 * cfg['n_splats'] / 1e6:.0f} MB resident scene, its centres and visible payload lines streamed per frame",

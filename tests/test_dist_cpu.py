@@ -145,3 +145,25 @@ def test_balanced_band_edges_cover_the_frame_and_even_out_the_load():
         if world == 8:
             assert max(per) < 0.25 * load.sum() < max(equal)      # equal-height bands leave most of it to two ranks
     assert vdist.balanced_band_edges(np.zeros(64), 4) == [0, 16, 32, 48, 64]
+
+
+def test_rebalance_band_edges_moves_rows_from_slow_bands_to_fast_ones():
+    """Feedback step of the band partition: with a cost model of a constant per band plus a share per row weight, a few
+    steps even the band times out; the bands always cover the frame and keep their minimum height."""
+    rng = np.random.default_rng(5)
+    h, world = 2160, 8
+    w = np.exp(-0.5 * ((np.arange(h) - 1100) / 250.0) ** 2) + 0.02          # row weights: most of the load mid-frame
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+
+    def times(e):
+        return [0.45 + 8.0 * (cum[e[g + 1]] - cum[e[g]]) / cum[-1] + 2e-4 * (e[g + 1] - e[g]) for g in range(world)]
+
+    e = [h * g // world for g in range(world + 1)]                            # equal rows: the middle bands carry the load
+    spread0 = max(times(e)) - min(times(e))
+    for _ in range(4):
+        e = vdist.rebalance_band_edges(e, times(e))
+        assert e[0] == 0 and e[-1] == h and all(b - a >= 8 for a, b in zip(e, e[1:]))
+    t = times(e)
+    assert max(t) - min(t) < 0.25 * spread0 and max(t) < 1.05 * np.mean(t)
+    assert vdist.rebalance_band_edges([0, 10, 20], [0.0, 0.0]) == [0, 10, 20]   # nothing measured: unchanged
+    assert vdist.rebalance_band_edges([0, 32, 64], [1.0, float("nan")]) == [0, 32, 64]

@@ -15,9 +15,11 @@ F = np.float32
 EPS = F(2e-5)
 
 
-def spatial_order(pos, bits=10):
-    """Stored order: stable sort by the 3 x `bits` Morton code of the centres quantised over mean +- 3 sigma (clamped to
-    the bounding box).  float64 here; the device does the same with integer moments (deterministic)."""
+def spatial_order(pos, lmax=None, bits=10):
+    """Stored order: stable sort by (size class, 3 x `bits` Morton code of the centres quantised over mean +- 3 sigma,
+    clamped to the bounding box); size class from lmax = the largest eigenvalue of the 3-D covariance: 3 sigma above 1/16
+    or 1/128 of the window's extent go first.  float64 here; the device does the same with integer moments
+    (deterministic)."""
     lo, hi = pos.min(0).astype(np.float64), pos.max(0).astype(np.float64)
     ext = np.maximum(hi - lo, 1e-30)
     u = (pos.astype(np.float64) - lo) / ext
@@ -28,6 +30,11 @@ def spatial_order(pos, bits=10):
     for bit in range(bits):
         for ax in range(3):
             key |= ((q[:, ax] >> bit) & 1) << (3 * bit + ax)
+    if lmax is not None:
+        w = ((b - a) * ext).max()
+        r2 = 9.0 * np.asarray(lmax, np.float64)
+        cls = (r2 * 16384.0 > w * w).astype(np.int64) + (r2 * 256.0 > w * w).astype(np.int64)
+        key |= (2 - cls) << (3 * bits)
     return np.argsort(key, kind="stable")
 
 

@@ -209,7 +209,7 @@ int spatial_reorder(vkgsb_renderer* r, uint32_t n) {
   a.max_n = n;
   a.keys = r->keys[0]; a.vals = r->slots[0]; a.keys_alt = r->keys_alt[0]; a.vals_alt = r->slots_alt[0];
   a.hist = r->ctrl[0]->hist_depth; a.tickets = r->ctrl[0]->sort_ticket; a.lookback = r->lookback_depth[0];
-  a.begin_bit = 0; a.npass = 4;  // 4 x 8 bits (the keys have 30): an even pass count, the result lands in keys / vals
+  a.begin_bit = 0; a.npass = 4;  // 4 x 8 bits: an even pass count, the result lands in keys / vals
   launch_sort(a, ls);
   CU_TRY(cudaMemcpyAsync(r->order, r->slots[0], static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, ls));
   const int pe = spatial_permute(r->scene, r->order, n, tmp, ls);

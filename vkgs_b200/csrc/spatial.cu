@@ -114,12 +114,17 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every t
   return v;
 }
 
-// pass 3: 30-bit Morton key of the centre quantised to 1024 cells per axis over mean +- 3 sigma of the box fractions
-// (a few far outliers must not squeeze the bulk of the scene into a handful of cells); outliers clamp to the border
-// cells, non-finite centres go last.  vals = 0, 1, 2, ...
+// pass 3: the sort key = size class (2 bits) | 30-bit Morton code of the centre quantised to 1024 cells per axis over
+// mean +- 3 sigma of the box fractions (a few far outliers must not squeeze the bulk of the scene into a handful of
+// cells); outliers clamp to the border cells, non-finite centres go last.  vals = 0, 1, 2, ...
+// Size classes: splats whose 3-sigma radius exceeds 1/16 (class 2) or 1/128 (class 1) of that window's extent are stored
+// in front of the rest, each class in Morton order.  A large splat reaches screen rows far from its centre: mixed in
+// with its small neighbours it would make their tile "cannot be decided from the box" for every screen band
+// (classify_tile takes the tile's largest lambda_max) and leave one or two visible splats per tile all over the band's
+// frustum.
 __global__ void __launch_bounds__(256) k_spatial_keys(SceneStorage sc, uint32_t n, const SpatialStats* st, uint32_t* keys,
                                                       uint32_t* vals) {
-  __shared__ float s_lo[3], s_scale[3];
+  __shared__ float s_lo[3], s_scale[3], s_ext[3];
   if (threadIdx.x < 3) {
     const int a = threadIdx.x;
     const double cnt = static_cast<double>(st->finite ? st->finite : 1ull);
@@ -129,11 +134,14 @@ __global__ void __launch_bounds__(256) k_spatial_keys(SceneStorage sc, uint32_t 
     const double lo = fmax(m - 3.0 * sd, 0.0), hi = fmin(m + 3.0 * sd, 1.0);
     s_lo[a] = static_cast<float>(lo);
     s_scale[a] = hi > lo ? static_cast<float>(1024.0 / (hi - lo)) : 0.f;
+    s_ext[a] = static_cast<float>(hi - lo) * (ord2f(st->max_ord[a]) - ord2f(st->min_ord[a]));  // the window in world units
   }
   __syncthreads();
   const uint32_t i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const float p[3] = {sc.x[i], sc.y[i], sc.z[i]};
+  const float ext = fmaxf(fmaxf(s_ext[0], s_ext[1]), s_ext[2]), r2 = 9.f * sc.tr[i];  // (3 sigma)^2; NaN -> class 0
+  const uint32_t cls = static_cast<uint32_t>(r2 * 16384.f > ext * ext) + static_cast<uint32_t>(r2 * 256.f > ext * ext);
   uint32_t key = 0x3fffffffu;
   if (finite3(p[0], p[1], p[2])) {
     uint32_t c[3];
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(256) k_spatial_keys(SceneStorage sc, uint32_t 
     }
     key = spread3(c[0]) | (spread3(c[1]) << 1) | (spread3(c[2]) << 2);
   }
-  keys[i] = key;
+  keys[i] = ((2u - cls) << 30) | key;  // the large ones first
   vals[i] = i;
 }
 

@@ -55,6 +55,31 @@ def balanced_band_edges(row_load, world: int, min_rows: int = 8) -> List[int]:
     return edges
 
 
+def rebalance_band_edges(edges, band_ms, min_rows: int = 8) -> List[int]:
+    """One feedback step of the band partition: `band_ms[g]` = measured time of band g = rows [edges[g], edges[g + 1]).
+    Every row of a band is charged an equal share of the band's time and the rows are re-cut into bands of equal charge
+    (the splat-centre histogram does not see what a band costs apart from its splats: the cull over the frustum, the
+    per-pixel work of the blend)."""
+    import numpy as np
+    edges = [int(e) for e in edges]
+    world, h = len(edges) - 1, edges[-1]
+    cost = np.zeros(h, np.float64)
+    for g in range(world):
+        rows = max(edges[g + 1] - edges[g], 1)
+        cost[edges[g]:edges[g + 1]] = max(float(band_ms[g]), 0.0) / rows
+    if not np.isfinite(cost).all() or cost.sum() <= 0.0:
+        return edges
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    out = [0]
+    for g in range(1, world):
+        y = int(np.searchsorted(cum, cum[-1] * g / world))
+        y = max(y, out[-1] + min_rows)
+        y = min(y, h - (world - g) * min_rows)
+        out.append(y)
+    out.append(h)
+    return out
+
+
 def gather_images(local, dst: int = 0, group=None):
     """Gather equally shaped uint8 image tensors [B,H,W,4] to rank `dst` (NCCL on GPUs, gloo in the CPU tests).
     Returns the list on dst, else None.  On one node bench.py prefers rendering straight into rank dst's memory
