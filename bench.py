@@ -61,9 +61,36 @@ def view_camera(cfg, i):
     return cam.projection_matrix(), cam.view_matrix(), cam.eye()
 
 
-def make_scene(cfg):
+def make_scene(cfg, dist=None, rank=0, world=1):
+    """The configuration's synthetic scene.  The 50 M-row scene of c5 (12.4 GB) is generated once per node: rank 0 writes
+    it to /dev/shm and the other ranks map it."""
     from vkgs_b200 import synth
-    return synth.scene_bicycle(cfg["n_splats"]) if cfg["scene"] == "bicycle" else synth.scene_large(cfg["n_splats"])
+    if cfg["scene"] == "bicycle":
+        return synth.scene_bicycle(cfg["n_splats"])
+    if world == 1 or dist is None:
+        return synth.scene_large(cfg["n_splats"])
+    token = [os.getpid()]
+    dist.broadcast_object_list(token, src=0)
+    path = f"/dev/shm/vkgsb_scene_{token[0]}.npy"
+    if rank == 0:
+        rows = synth.scene_large(cfg["n_splats"])
+        np.save(path + ".tmp.npy", rows)
+        os.rename(path + ".tmp.npy", path)
+    else:
+        while not os.path.exists(path):
+            time.sleep(0.05)
+        rows = np.load(path, mmap_mode="r")
+    return rows
+
+
+def drop_shared_scene(dist, rank, world):
+    """After every rank has uploaded the scene: remove rank 0's copy in /dev/shm."""
+    if world > 1:
+        dist.barrier()
+        if rank == 0:
+            import glob
+            for f in glob.glob(f"/dev/shm/vkgsb_scene_{os.getpid()}.npy*"):
+                os.remove(f)
 
 
 class ClockSampler:
@@ -361,11 +388,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     W_, H_ = cfg["width"], cfg["height"]
-    rows = make_scene(cfg)
+    rows = make_scene(cfg, dist if world > 1 else None, rank, world)
     r = vkgs_b200.Renderer(device=local, max_splats=cfg["n_splats"], max_width=W_, max_height=H_, max_pairs=cfg["max_pairs"])
     if os.environ.get("VKGSB_SPATIAL_ORDER"):      # experiments: 0 keeps the file's order (no spatial order of the stored scene)
         r.set_option(L.OPT_SPATIAL_ORDER, int(os.environ["VKGSB_SPATIAL_ORDER"]))
     r.upload_splats(rows)
+    if cfg["scene"] != "bicycle":
+        drop_shared_scene(dist, rank, world)
     if not (world == 1 and not args.no_cpu_baseline and args.config == "c2"):
         del rows
     r.set_viewport(W_, H_)

@@ -167,3 +167,34 @@ def test_rebalance_band_edges_moves_rows_from_slow_bands_to_fast_ones():
     assert max(t) - min(t) < 0.25 * spread0 and max(t) < 1.05 * np.mean(t)
     assert vdist.rebalance_band_edges([0, 10, 20], [0.0, 0.0]) == [0, 10, 20]   # nothing measured: unchanged
     assert vdist.rebalance_band_edges([0, 32, 64], [1.0, float("nan")]) == [0, 32, 64]
+
+
+def _scene_worker(rank, world, port, out):
+    import bench
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfg = dict(bench.CONFIGS["c5"])
+        cfg["n_splats"] = 120_000
+        rows = bench.make_scene(cfg, dist, rank, world)          # rank 0 generates, rank 1 maps rank 0's copy
+        np.save(f"{out}.{rank}.npy", np.asarray(rows))
+        kind = type(rows).__name__
+        bench.drop_shared_scene(dist, rank, world)
+        dist.barrier()
+        import glob
+        assert not glob.glob("/dev/shm/vkgsb_scene_*") or rank != 0
+        with open(f"{out}.{rank}.txt", "w") as f:
+            f.write(kind)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_c5_scene_is_generated_once_per_node_and_is_thread_count_independent(tmp_path):
+    out = str(tmp_path / "scene")
+    mp.spawn(_scene_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    want = synth.scene_large(120_000, threads=1)
+    assert np.array_equal(synth.scene_large(120_000, chunk=1_000_000, threads=3), want)
+    for rank in range(2):
+        assert np.array_equal(np.load(f"{out}.{rank}.npy"), want)
+    assert open(f"{out}.1.txt").read() == "memmap"
