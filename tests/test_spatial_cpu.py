@@ -23,8 +23,10 @@ VIEWS = [(1.5, 70.0, 30.0, 60.0), (0.4, 85.0, 200.0, 60.0), (8.0, 20.0, 10.0, 35
 def ordered_scene():
     rows = synth.scene_bicycle(300_000, seed=77)
     sc = O.activate(rows, synth.STANDARD_OFFSETS)
-    order = SM.spatial_order(sc.pos)
+    lmax = np.exp(2.0 * rows[:, synth._COL["scale_0"]:synth._COL["scale_2"] + 1].max(1))   # largest eigenvalue of Sigma
+    order = SM.spatial_order(sc.pos, lmax)                        # large splats first, Morton order inside each class
     assert np.array_equal(np.sort(order), np.arange(len(rows)))
+    assert lmax[order[:256]].min() > np.median(lmax)
     return O.Scene(sc.pos[order], sc.cov[order], sc.opacity[order], sc.sh[order])
 
 

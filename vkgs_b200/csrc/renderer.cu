@@ -201,23 +201,32 @@ int spatial_reorder(vkgsb_renderer* r, uint32_t n) {
     cudaGetLastError();
     return VKGSB_OK;
   }
-  CU_TRY(cudaMemsetAsync(r->zero_region[0], 0, r->zero_bytes, ls));
-  launch_spatial_keys(r->scene, n, r->d_stats, r->keys[0], r->slots[0], ls);
-  CU_TRY(cudaMemcpyAsync(&r->ctrl[0]->visible_count, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, ls));
-  SortArgs a{};
-  a.d_count = &r->ctrl[0]->visible_count;
-  a.max_n = n;
-  a.keys = r->keys[0]; a.vals = r->slots[0]; a.keys_alt = r->keys_alt[0]; a.vals_alt = r->slots_alt[0];
-  a.hist = r->ctrl[0]->hist_depth; a.tickets = r->ctrl[0]->sort_ticket; a.lookback = r->lookback_depth[0];
-  a.begin_bit = 0; a.npass = 4;  // 4 x 8 bits: an even pass count, the result lands in keys / vals
-  launch_sort(a, ls);
-  CU_TRY(cudaMemcpyAsync(r->order, r->slots[0], static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, ls));
-  const int pe = spatial_permute(r->scene, r->order, n, tmp, ls);
-  launch_tile_boxes(r->scene, n, 0, (n + 255u) / 256u, r->boxes, ls);
-  cudaError_t e = cudaStreamSynchronize(ls);
+  auto run = [&]() -> cudaError_t {
+    cudaError_t e = cudaMemsetAsync(r->zero_region[0], 0, r->zero_bytes, ls);
+    if (e != cudaSuccess) return e;
+    launch_spatial_keys(r->scene, n, r->d_stats, r->keys[0], r->slots[0], ls);
+    e = cudaMemcpyAsync(&r->ctrl[0]->visible_count, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, ls);
+    if (e != cudaSuccess) return e;
+    SortArgs a{};
+    a.d_count = &r->ctrl[0]->visible_count;
+    a.max_n = n;
+    a.keys = r->keys[0]; a.vals = r->slots[0]; a.keys_alt = r->keys_alt[0]; a.vals_alt = r->slots_alt[0];
+    a.hist = r->ctrl[0]->hist_depth; a.tickets = r->ctrl[0]->sort_ticket; a.lookback = r->lookback_depth[0];
+    a.begin_bit = 0; a.npass = 4;  // 4 x 8 bits: an even pass count, the result lands in keys / vals
+    launch_sort(a, ls);
+    e = cudaMemcpyAsync(r->order, r->slots[0], static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, ls);
+    if (e != cudaSuccess) return e;
+    if (spatial_permute(r->scene, r->order, n, tmp, ls)) return cudaErrorLaunchFailure;
+    launch_tile_boxes(r->scene, n, 0, (n + 255u) / 256u, r->boxes, ls);
+    e = cudaStreamSynchronize(ls);
+    return e != cudaSuccess ? e : cudaGetLastError();
+  };
+  const cudaError_t e = run();
   cudaFree(tmp);
-  if (pe || e != cudaSuccess) return fail(VKGSB_ERR_CUDA, std::string("spatial reorder: ") + cudaGetErrorString(e));
-  CU_TRY(cudaGetLastError());
+  if (e != cudaSuccess) {
+    r->scene_n.store(0);  // the arrays may be half permuted: nothing is resident
+    return fail(VKGSB_ERR_CUDA, std::string("spatial reorder: ") + cudaGetErrorString(e));
+  }
   return VKGSB_OK;
 }
 
