@@ -33,7 +33,8 @@ sys.path.insert(0, ROOT)
 
 UNIT = "frames/s"
 PARAM_BYTES = 560                 # sizeof(FrameParams): the per-frame host->device upload (a kernel argument)
-E2E_BATCH = 8                     # views per vkgsb_draw_batch call in the end-to-end leg
+E2E_BATCH = 32                    # views per vkgsb_draw_batch call in the end-to-end leg (an orbit is submitted in one
+                                  # call when it has no more views: the call returns when every image is in host memory)
 SMEM_BYTES_PER_ENTRY = 52         # blend stage: 3 x float4 raster record + 4-byte sub-tile mask per staged list entry
 FP32_INSTR_PER_FRAGMENT = 20      # algorithmic FP32 instructions per fragment (the blend roofline's unit)
 
