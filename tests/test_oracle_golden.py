@@ -59,7 +59,9 @@ def test_projection_matches_shader(golden, variant):
     inst = O.project(sc, golden["sorted_index"], cam, variant)
     ref = golden["instances"]
     assert not np.isnan(inst[:, USE]).any() and not np.isnan(ref[:, USE]).any()
-    for cols, tol in ((slice(0, 3), 2e-6), (slice(4, 8), 2e-5), (slice(8, 11), 2e-6)):
+    # instance records within rel 1e-5 of the reference shader (measured: <= 2.2e-6 on the RS columns,
+    # <= 7e-7 elsewhere)
+    for cols, tol in ((slice(0, 3), 2e-6), (slice(4, 8), 1e-5), (slice(8, 11), 2e-6)):
         scale = np.abs(ref[:, cols]).max(axis=1, keepdims=True) + 1e-12
         assert (np.abs(inst[:, cols] - ref[:, cols]) / scale).max() < tol
     assert np.array_equal(inst[:, 11], ref[:, 11])
