@@ -3,15 +3,15 @@
 // Replaces third_party/vulkan_radix_sort (vrdxCmdSortKeyValueIndirect, src/vk_radix_sort.cc:249-416 with
 // upsweep/spine/downsweep.slang): same contract - ascending, STABLE, 8-bit digits, count taken from a device buffer,
 // surplus workgroups exit - but one-sweep instead of reduce-then-scan: a single histogram kernel for all digits
-// (4 B/key) and one chained-scan scatter kernel per digit (16 B/pair), 68 B/pair over 4 passes against the
-// reference's 80.  Partition prefixes travel through a decoupled look-back array instead of the
-// spine kernel.
+// (4 B/key) and one scatter kernel per digit (16 B/pair), 68 B/pair over 4 passes against the reference's 80
+// (SURVEY.md §8a-5).  Partition prefixes come from an 8-ary tree of partition aggregates (a depth sort is ONE wave of
+// partitions that all post at once: no chained look-back), not from a spine kernel.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vkgsb {
 
-constexpr int kSortThreads = 256;  // thread t owns the digits [t * DPT, (t + 1) * DPT) in the scan / look-back steps
+constexpr int kSortThreads = 256;  // thread t owns the digits [t * DPT, (t + 1) * DPT) in the scan / aggregate-tree steps
 constexpr int kSortItems = 16;
 constexpr int kSortPart = kSortThreads * kSortItems;  // 4096 pairs per partition (PARTITION_SIZE, constants.slang:5)
 constexpr int kSortWarps = kSortThreads / 32;
